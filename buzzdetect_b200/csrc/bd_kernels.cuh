@@ -1,0 +1,75 @@
+// Launch-function declarations shared by the translation units of libbuzzdetect_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cstdint>
+#include <cstddef>
+
+namespace bd {
+
+constexpr int kWin = 400;          // 25 ms @ 16 kHz         (embedders/yamnet/params.py:26)
+constexpr int kHop = 160;          // 10 ms                  (params.py:27)
+constexpr int kFft = 512;
+constexpr int kBins = 257;
+constexpr int kMel = 64;           // params.py:28
+constexpr int kPatchFrames = 96;   // 0.96 s                 (params.py:32)
+constexpr int kMinSamples = 15600; // Const_5 of the SavedModel graphs
+constexpr int kMelNnzMax = 512;    // 461 non-zeros in the shipped mel matrix
+constexpr int kEmb = 1024;
+constexpr int kMaxClasses = 32;
+
+struct FrontendTables {            // device-resident, built once per engine
+    float window[kWin];            // periodic Hann exactly as the graph computes it in float32
+    int mel_start[kMel];           // first non-zero spectrogram bin of each mel band
+    int mel_len[kMel];             // number of consecutive bins
+    int mel_off[kMel];             // offset of the band's weights in mel_w
+    float mel_w[kMelNnzMax];
+};
+
+// ---- frontend.cu
+size_t frontend_smem_bytes();
+cudaError_t frontend_init_device();
+cudaError_t launch_logmel(const float* x, long long n_valid, long long frame_begin, int n_frames,
+                          const FrontendTables* tab, float* logmel, int num_sms, cudaStream_t stream);
+
+// ---- layers.cu
+// conv 3x3 stride 2 SAME (pad 0 before / 1 after), 1 -> 32 channels, folded BN + ReLU.  in: log-mel rows, patch p
+// starts at row p*hop_frames of `logmel` (patches are views, never copied).  out: [P,48,32,32] float32 NHWC.
+cudaError_t launch_conv1(const float* logmel, int hop_frames, int P, const float* w9x32, const float* b32,
+                         float* out, cudaStream_t stream);
+// depthwise 3x3 (stride 1: pad 1/1, stride 2: pad 0/1), folded BN + ReLU.  in [P,H,W,C] float32 NHWC.
+// out_mode 0: float32 plane `out_f32` [P*Ho*Wo, C]
+// out_mode 1: fp16 hi plane only            (single-pass tensor-core GEMM operand)
+// out_mode 2: fp16 hi + lo planes, x ~= hi + lo  (3-product split GEMM operand)
+cudaError_t launch_depthwise(const float* in, int P, int H, int W, int C, int stride, const float* w9xC,
+                             const float* bC, int out_mode, float* out_f32, __half* out_hi, __half* out_lo,
+                             cudaStream_t stream);
+// reference-precision pointwise conv on CUDA cores: C[M,N] = relu(A[M,K] * Bt[N,K]^T + bias)
+cudaError_t launch_pw_simt(const float* A, const float* Bt, const float* bias, float* C, int M, int N, int K,
+                           cudaStream_t stream);
+// global average pool over `rows_per_patch` rows + dense head: y [P*rows, 1024] -> emb [P,1024] (optional),
+// act [P, n_classes] = emb @ Wh[1024, n_classes] + bh
+cudaError_t launch_pool_head(const float* y, int P, int rows_per_patch, const float* Wh, const float* bh,
+                             int n_classes, float* emb, float* act, cudaStream_t stream);
+
+// ---- pw_gemm_sm100.cu  (tcgen05 / TMEM / TMA)
+struct PwGemmPlan {
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    int M_max, N, K, block_n, nsplit;
+};
+cudaError_t pw_gemm_init_device();
+// Build TMA descriptors for A planes [M_max, K] (row stride lda halfs) and weight planes [N, K].
+// block_n: 64/128/256, or 0 to choose automatically.
+cudaError_t pw_gemm_make_plan(PwGemmPlan* plan, const __half* a_hi, const __half* a_lo, int M_max, int K,
+                              const __half* b_hi, const __half* b_lo, int N, int nsplit, int block_n,
+                              const char** err);
+cudaError_t launch_pw_gemm(const PwGemmPlan& plan, const float* bias, float* C, int M, int num_sms,
+                           cudaStream_t stream);
+
+// ---- resample.cu
+cudaError_t launch_resample(const void* in, int in_fmt /*0 f32, 1 s16*/, int channels, long long n_in_frames,
+                            int up, int down, const float* taps, int taps_per_phase, float* out, long long n_out,
+                            cudaStream_t stream);
+
+}  // namespace bd

@@ -1,0 +1,835 @@
+// bd_engine: device buffers, weight upload, the chunk pipeline and the C ABI (include/buzzdetect_b200.h).
+//
+// One engine = one inferer (reference: one model instance per WorkerInferer thread, src/inference/worker.py:21).
+// A chunk of 16 kHz audio goes through
+//     frontend -> conv1 -> 13 x (depthwise -> pointwise) -> mean(H,W) -> dense head
+// in sub-batches sized so that every inter-layer activation stays resident in the 126 MB L2:
+//   * "early" phase (frontend .. layer-7 depthwise, up to 384 KB of activations per patch): early_patches at a time
+//   * "late"  phase (layer-7 pointwise .. head, <= 48 KB per patch): late_patches at a time
+// The same small buffers are re-used by every sub-batch, so dirty lines are overwritten in L2 instead of being
+// written back; HBM traffic is essentially the audio in and the activations out.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/buzzdetect_b200.h"
+#include "bd_kernels.cuh"
+
+using namespace bd;
+
+namespace {
+
+struct LayerDev {
+    bd_layer_desc d;
+    int h_out, w_out;
+    const float* dw_w = nullptr;    // device pointers into folded blob
+    const float* dw_b = nullptr;
+    const float* w = nullptr;       // conv: [9,32]; sep: [cout,cin] float32
+    const float* b = nullptr;
+    __half* w_hi = nullptr;         // [cout,cin] fp16 planes (tensor-core modes)
+    __half* w_lo = nullptr;
+    PwGemmPlan plan;
+    bool late = false;              // pointwise runs in the late phase
+};
+
+struct Slot {
+    float* d_in = nullptr;
+    int64_t in_cap = 0;
+    float* d_act = nullptr;
+    float* d_emb = nullptr;
+    int64_t out_cap = 0;            // patches
+    cudaEvent_t ev_in = nullptr, ev_comp = nullptr, ev_out = nullptr;
+    bool busy = false;
+};
+
+struct GraphKey {
+    const float* x; int64_t n; int hop; float* act; float* emb;
+    bool operator<(const GraphKey& o) const {
+        return std::tie(x, n, hop, act, emb) < std::tie(o.x, o.n, o.hop, o.act, o.emb);
+    }
+};
+
+}  // namespace
+
+struct bd_engine {
+    int device = 0, num_sms = 148, precision = BD_PRECISION_FP16X3;
+    int S1 = 64, S2 = 512, n_classes = 13;
+    bool use_graph = true;
+    cudaStream_t s_compute = nullptr, s_in = nullptr, s_out = nullptr;
+    float* d_folded = nullptr;
+    FrontendTables* d_tab = nullptr;
+    float* d_headW = nullptr;
+    float* d_headB = nullptr;
+    std::vector<LayerDev> layers;
+    // activations
+    float* d_logmel = nullptr;
+    float* d_F_early = nullptr;
+    unsigned char* d_H_early = nullptr;
+    size_t H_early_plane_bytes = 0;      // offset of the lo plane
+    float* d_F_late = nullptr;
+    unsigned char* d_H_late = nullptr;
+    size_t H_late_plane_bytes = 0;
+    std::vector<Slot> slots;
+    std::map<GraphKey, cudaGraphExec_t> graphs;
+    std::map<GraphKey, int64_t> graph_launches;
+    int64_t launch_count = 0;
+    // profiling hooks (bd_profile_device)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;
+    std::vector<int> prof_cat;
+    // resampler filter cache: (src_rate) -> device taps
+    struct Resampler { int up, down, taps_per_phase; float* d_taps; };
+    std::map<int, Resampler> resamplers;
+    std::string last_error;
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+#define BD_CHECK(e, expr)                                                                       \
+    do {                                                                                        \
+        cudaError_t _err = (expr);                                                              \
+        if (_err != cudaSuccess) {                                                              \
+            (e)->last_error = std::string(#expr) + ": " + cudaGetErrorString(_err);             \
+            return 1;                                                                           \
+        }                                                                                       \
+    } while (0)
+
+int fail(bd_engine* e, const std::string& msg) {
+    e->last_error = msg;
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------ framing math
+// embedders/yamnet/features.py:82-108 -- the hop count is ceil(float32(after) / float32(hop)).
+void frames_for(int64_t n, int hop_frames, int64_t* n_padded, int64_t* n_frames, int64_t* n_patches) {
+    const int64_t hop_samples = static_cast<int64_t>(hop_frames) * kHop;
+    int64_t pad = std::max<int64_t>(0, kMinSamples - n);
+    const int64_t n2 = std::max<int64_t>(n, kMinSamples);
+    const int64_t after = n2 - kMinSamples;
+    const float q = static_cast<float>(after) / static_cast<float>(hop_samples);
+    const int64_t hops = static_cast<int64_t>(std::ceil(q));
+    pad += hop_samples * hops - after;
+    const int64_t np = n + pad;
+    const int64_t f = np >= kWin ? 1 + (np - kWin) / kHop : 0;
+    const int64_t p = f >= kPatchFrames ? 1 + (f - kPatchFrames) / hop_frames : 0;
+    if (n_padded) *n_padded = np;
+    if (n_frames) *n_frames = f;
+    if (n_patches) *n_patches = p;
+}
+
+// ------------------------------------------------------------------------------------------ profiling hooks
+enum Cat { CAT_FRONTEND = 0, CAT_CONV1 = 1, CAT_DW = 2, CAT_PW = 3, CAT_POOL = 4 };
+
+void mark(bd_engine* e, int cat, cudaStream_t st) {
+    e->launch_count++;
+    if (!e->profiling) return;
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    cudaEventRecord(ev, st);
+    e->prof_events.push_back(ev);
+    e->prof_cat.push_back(cat);
+}
+
+// ------------------------------------------------------------------------------------------ the pipeline
+// Enqueue the whole chunk on `st`.  x: device audio, n samples.  Outputs are device pointers.
+// stop_stage >= 0 (debug): stop after that stage of the FIRST early sub-batch (see bd_debug_stage).
+int enqueue_chunk(bd_engine* e, const float* x, int64_t n, int hop_frames, float* d_act, float* d_emb,
+                  int64_t P, cudaStream_t st, int stop_stage = -1) {
+    const int prec = e->precision;
+    const int dw_mode = prec == BD_PRECISION_FP32_SIMT ? 0 : (prec == BD_PRECISION_FP16X1 ? 1 : 2);
+    for (int64_t big = 0; big < P; big += e->S2) {
+        const int nb = static_cast<int>(std::min<int64_t>(e->S2, P - big));
+        // ---------------- early phase
+        for (int small = 0; small < nb; small += e->S1) {
+            const int ns = std::min(e->S1, nb - small);
+            const int64_t p0 = big + small;
+            const int n_fr = (ns - 1) * hop_frames + kPatchFrames;
+            BD_CHECK(e, launch_logmel(x, n, p0 * hop_frames, n_fr, e->d_tab, e->d_logmel, e->num_sms, st));
+            mark(e, CAT_FRONTEND, st);
+            if (stop_stage == 0) return 0;
+            const LayerDev& l1 = e->layers[0];
+            BD_CHECK(e, launch_conv1(e->d_logmel, hop_frames, ns, l1.w, l1.b, e->d_F_early, st));
+            mark(e, CAT_CONV1, st);
+            if (stop_stage == 1) return 0;
+            for (int L = 1; L < BD_N_LAYERS; ++L) {
+                const LayerDev& l = e->layers[L];
+                const bool to_late = l.late;          // this depthwise feeds the late phase
+                unsigned char* H = to_late ? e->d_H_late : e->d_H_early;
+                const size_t plane = to_late ? e->H_late_plane_bytes : e->H_early_plane_bytes;
+                const int64_t row_off = to_late ? static_cast<int64_t>(small) * l.h_out * l.w_out : 0;
+                float* o32 = reinterpret_cast<float*>(H) + row_off * l.d.cin;
+                __half* ohi = reinterpret_cast<__half*>(H) + row_off * l.d.cin;
+                __half* olo = reinterpret_cast<__half*>(H + plane) + row_off * l.d.cin;
+                BD_CHECK(e, launch_depthwise(e->d_F_early, ns, l.d.h_in, l.d.w_in, l.d.cin, l.d.stride, l.dw_w, l.dw_b,
+                                             dw_mode, o32, ohi, olo, st));
+                mark(e, CAT_DW, st);
+                if (stop_stage == 2 * L) return 0;
+                if (to_late) break;
+                const int M = ns * l.h_out * l.w_out;
+                if (prec == BD_PRECISION_FP32_SIMT) {
+                    BD_CHECK(e, launch_pw_simt(reinterpret_cast<const float*>(H), l.w, l.b, e->d_F_early, M, l.d.cout,
+                                               l.d.cin, st));
+                } else {
+                    BD_CHECK(e, launch_pw_gemm(l.plan, l.b, e->d_F_early, M, e->num_sms, st));
+                }
+                mark(e, CAT_PW, st);
+                if (stop_stage == 2 * L + 1) return 0;
+            }
+        }
+        // ---------------- late phase
+        int first_late = 0;
+        for (int L = 1; L < BD_N_LAYERS; ++L) if (e->layers[L].late) { first_late = L; break; }
+        for (int L = first_late; L < BD_N_LAYERS; ++L) {
+            const LayerDev& l = e->layers[L];
+            if (L != first_late) {
+                BD_CHECK(e, launch_depthwise(e->d_F_late, nb, l.d.h_in, l.d.w_in, l.d.cin, l.d.stride, l.dw_w, l.dw_b,
+                                             dw_mode, reinterpret_cast<float*>(e->d_H_late),
+                                             reinterpret_cast<__half*>(e->d_H_late),
+                                             reinterpret_cast<__half*>(e->d_H_late + e->H_late_plane_bytes), st));
+                mark(e, CAT_DW, st);
+                if (stop_stage == 2 * L) return 0;
+            }
+            const int M = nb * l.h_out * l.w_out;
+            if (prec == BD_PRECISION_FP32_SIMT) {
+                BD_CHECK(e, launch_pw_simt(reinterpret_cast<const float*>(e->d_H_late), l.w, l.b, e->d_F_late, M,
+                                           l.d.cout, l.d.cin, st));
+            } else {
+                BD_CHECK(e, launch_pw_gemm(l.plan, l.b, e->d_F_late, M, e->num_sms, st));
+            }
+            mark(e, CAT_PW, st);
+            if (stop_stage == 2 * L + 1) return 0;
+        }
+        const LayerDev& last = e->layers[BD_N_LAYERS - 1];
+        BD_CHECK(e, launch_pool_head(e->d_F_late, nb, last.h_out * last.w_out, e->d_headW, e->d_headB, e->n_classes,
+                                     d_emb ? d_emb + big * kEmb : nullptr, d_act + big * e->n_classes, st));
+        mark(e, CAT_POOL, st);
+    }
+    return 0;
+}
+
+// Run (or replay) the chunk on s_compute.
+int run_chunk(bd_engine* e, const float* x, int64_t n, int hop_frames, float* d_act, float* d_emb, int64_t P) {
+    if (P <= 0) return 0;
+    if (!e->use_graph || e->profiling) return enqueue_chunk(e, x, n, hop_frames, d_act, d_emb, P, e->s_compute);
+    GraphKey key{x, n, hop_frames, d_act, d_emb};
+    auto it = e->graphs.find(key);
+    if (it == e->graphs.end()) {
+        if (e->graphs.size() >= 32) {           // bounded cache
+            for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+            e->graphs.clear();
+            e->graph_launches.clear();
+        }
+        const int64_t before = e->launch_count;
+        BD_CHECK(e, cudaStreamBeginCapture(e->s_compute, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_chunk(e, x, n, hop_frames, d_act, d_emb, P, e->s_compute);
+        cudaGraph_t g = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(e->s_compute, &g);
+        const int64_t per_graph = e->launch_count - before;
+        e->launch_count = before;
+        if (rc != 0) { if (g) cudaGraphDestroy(g); return rc; }
+        BD_CHECK(e, ce);
+        cudaGraphExec_t ge = nullptr;
+        cudaError_t ie = cudaGraphInstantiate(&ge, g, 0);
+        cudaGraphDestroy(g);
+        BD_CHECK(e, ie);
+        it = e->graphs.emplace(key, ge).first;
+        e->graph_launches[key] = per_graph;
+    }
+    BD_CHECK(e, cudaGraphLaunch(it->second, e->s_compute));
+    e->launch_count += e->graph_launches[key];
+    return 0;
+}
+
+int ensure_slot(bd_engine* e, Slot& s, int64_t n, int64_t P) {
+    if (n > s.in_cap) {
+        if (s.d_in) cudaFree(s.d_in);
+        s.d_in = nullptr;
+        const int64_t cap = ((n + 4095) / 4096) * 4096 + 64;
+        BD_CHECK(e, cudaMalloc(&s.d_in, cap * sizeof(float)));
+        s.in_cap = cap;
+    }
+    if (P > s.out_cap) {
+        if (s.d_act) cudaFree(s.d_act);
+        if (s.d_emb) cudaFree(s.d_emb);
+        s.d_act = s.d_emb = nullptr;
+        const int64_t cap = ((P + 255) / 256) * 256;
+        BD_CHECK(e, cudaMalloc(&s.d_act, cap * e->n_classes * sizeof(float)));
+        BD_CHECK(e, cudaMalloc(&s.d_emb, cap * kEmb * sizeof(float)));
+        s.out_cap = cap;
+    }
+    return 0;
+}
+
+// fp32 -> hi/lo fp16 planes on the host (weights only; done once)
+void split_f16(const float* src, size_t n, std::vector<__half>& hi, std::vector<__half>& lo) {
+    hi.resize(n);
+    lo.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+        const __half h = __float2half_rn(src[i]);
+        hi[i] = h;
+        lo[i] = __float2half_rn(src[i] - __half2float(h));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ resampler design
+double bessel_i0(double x) {
+    double sum = 1.0, term = 1.0;
+    const double q = x * x / 4.0;
+    for (int k = 1; k < 200; ++k) {
+        term *= q / (static_cast<double>(k) * k);
+        sum += term;
+        if (term < 1e-18 * sum) break;
+    }
+    return sum;
+}
+
+int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; }
+
+}  // namespace
+
+// ============================================================================================ C ABI
+extern "C" {
+
+int32_t bd_abi_version(void) { return BD_ABI_VERSION; }
+
+int32_t bd_frames_for(int64_t n_samples, int32_t hop_frames, int64_t* n_padded, int64_t* n_stft_frames,
+                      int64_t* n_patches) {
+    if (n_samples < 0 || hop_frames < 1 || hop_frames > kPatchFrames) return 1;
+    frames_for(n_samples, hop_frames, n_padded, n_stft_frames, n_patches);
+    return 0;
+}
+
+const char* bd_last_error(const bd_engine* e) { return e ? e->last_error.c_str() : g_create_error.c_str(); }
+
+int64_t bd_launch_count(const bd_engine* e) { return e ? e->launch_count : 0; }
+
+void bd_engine_destroy(bd_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+    for (auto& s : e->slots) {
+        cudaFree(s.d_in); cudaFree(s.d_act); cudaFree(s.d_emb);
+        if (s.ev_in) cudaEventDestroy(s.ev_in);
+        if (s.ev_comp) cudaEventDestroy(s.ev_comp);
+        if (s.ev_out) cudaEventDestroy(s.ev_out);
+    }
+    for (auto& l : e->layers) { cudaFree(l.w_hi); cudaFree(l.w_lo); }
+    for (auto& kv : e->resamplers) cudaFree(kv.second.d_taps);
+    cudaFree(e->d_folded); cudaFree(e->d_tab); cudaFree(e->d_headW); cudaFree(e->d_headB);
+    cudaFree(e->d_logmel); cudaFree(e->d_F_early); cudaFree(e->d_H_early); cudaFree(e->d_F_late); cudaFree(e->d_H_late);
+    if (e->s_compute) cudaStreamDestroy(e->s_compute);
+    if (e->s_in) cudaStreamDestroy(e->s_in);
+    if (e->s_out) cudaStreamDestroy(e->s_out);
+    delete e;
+}
+
+int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** out, char* err, size_t err_len) {
+    auto set_err = [&](const std::string& m) {
+        g_create_error = m;
+        if (err && err_len) { std::strncpy(err, m.c_str(), err_len - 1); err[err_len - 1] = 0; }
+        return 1;
+    };
+    if (!cfg || !w || !out) return set_err("null argument");
+    *out = nullptr;
+    if (cfg->precision != BD_PRECISION_FP32_SIMT && cfg->precision != BD_PRECISION_FP16X1 &&
+        cfg->precision != BD_PRECISION_FP16X3)
+        return set_err("precision must be 0 (fp32 SIMT), 1 (fp16) or 3 (fp16 x3 split)");
+    if (w->n_classes < 1 || w->n_classes > kMaxClasses) return set_err("n_classes out of range");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return set_err(std::string("no CUDA device: ") + cudaGetErrorString(ce) + " (this library has no CPU path)");
+    if (cfg->device < 0 || cfg->device >= ndev) return set_err("device ordinal out of range");
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return set_err("cudaSetDevice failed");
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, cfg->device);
+    if (prop.major != 10) return set_err(std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                          "; this library is built for sm_100a (B200) only");
+
+    bd_engine* e = new bd_engine();
+    e->device = cfg->device;
+    e->num_sms = prop.multiProcessorCount;
+    e->precision = cfg->precision;
+    e->S1 = cfg->early_patches > 0 ? cfg->early_patches : 64;
+    e->S2 = cfg->late_patches > 0 ? cfg->late_patches : 512;
+    e->S2 = std::max(e->S1, (e->S2 / e->S1) * e->S1);           // late batch = whole number of early batches
+    e->use_graph = cfg->use_graph != 0;
+    e->n_classes = w->n_classes;
+    auto bail = [&](const std::string& m) { std::string mm = m; bd_engine_destroy(e); return set_err(mm); };
+#define BD_CREATE(expr)                                                                      \
+    do {                                                                                     \
+        cudaError_t _err = (expr);                                                           \
+        if (_err != cudaSuccess) return bail(std::string(#expr) + ": " + cudaGetErrorString(_err)); \
+    } while (0)
+
+    BD_CREATE(cudaStreamCreateWithFlags(&e->s_compute, cudaStreamNonBlocking));
+    BD_CREATE(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+    BD_CREATE(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+    BD_CREATE(frontend_init_device());
+    if (e->precision != BD_PRECISION_FP32_SIMT) BD_CREATE(pw_gemm_init_device());
+
+    // ---- weights
+    BD_CREATE(cudaMalloc(&e->d_folded, w->folded_len * sizeof(float)));
+    BD_CREATE(cudaMemcpy(e->d_folded, w->folded, w->folded_len * sizeof(float), cudaMemcpyHostToDevice));
+    BD_CREATE(cudaMalloc(&e->d_headW, sizeof(float) * kEmb * w->n_classes));
+    BD_CREATE(cudaMemcpy(e->d_headW, w->head_kernel, sizeof(float) * kEmb * w->n_classes, cudaMemcpyHostToDevice));
+    BD_CREATE(cudaMalloc(&e->d_headB, sizeof(float) * w->n_classes));
+    BD_CREATE(cudaMemcpy(e->d_headB, w->head_bias, sizeof(float) * w->n_classes, cudaMemcpyHostToDevice));
+
+    // ---- frontend tables: window as given; mel -> per-band contiguous non-zero runs
+    {
+        FrontendTables t;
+        std::memset(&t, 0, sizeof(t));
+        std::memcpy(t.window, w->window, sizeof(float) * kWin);
+        int off = 0;
+        for (int m = 0; m < kMel; ++m) {
+            int first = -1, lastnz = -1;
+            for (int k = 0; k < kBins; ++k)
+                if (w->mel[k * kMel + m] != 0.f) { if (first < 0) first = k; lastnz = k; }
+            if (first < 0) { first = 0; lastnz = -1; }
+            const int len = lastnz - first + 1;
+            if (off + len > kMelNnzMax) return bail("mel matrix has too many non-zeros for the sparse table");
+            t.mel_start[m] = first; t.mel_len[m] = len; t.mel_off[m] = off;
+            for (int j = 0; j < len; ++j) t.mel_w[off + j] = w->mel[(first + j) * kMel + m];
+            off += len;
+        }
+        BD_CREATE(cudaMalloc(&e->d_tab, sizeof(FrontendTables)));
+        BD_CREATE(cudaMemcpy(e->d_tab, &t, sizeof(t), cudaMemcpyHostToDevice));
+    }
+
+    // ---- layers + buffer plan
+    size_t f_early = 0, h_early = 0, f_late = 0, h_late = 0;    // elements per patch
+    e->layers.resize(BD_N_LAYERS);
+    int first_late = 6;                                          // layer 7 (index 6): its depthwise output feeds the late phase
+    for (int L = 0; L < BD_N_LAYERS; ++L) {
+        LayerDev& l = e->layers[L];
+        l.d = w->layers[L];
+        if ((L == 0) != (l.d.kind == 0)) return bail("layer table: layer 1 must be the conv, the rest separable");
+        l.h_out = l.d.h_in / l.d.stride;
+        l.w_out = l.d.w_in / l.d.stride;
+        l.late = L >= first_late;
+        auto ptr = [&](int64_t o) -> const float* { return o >= 0 ? e->d_folded + o : nullptr; };
+        l.dw_w = ptr(l.d.dw_w); l.dw_b = ptr(l.d.dw_b); l.w = ptr(l.d.w); l.b = ptr(l.d.b);
+        const size_t out_px = static_cast<size_t>(l.h_out) * l.w_out;
+        if (L == 0) {
+            if (l.d.cin != 1 || l.d.cout != 32 || l.d.h_in != 96 || l.d.w_in != 64 || l.d.stride != 2)
+                return bail("layer 1 must be 3x3/2 conv 1->32 on a 96x64 patch");
+            f_early = std::max(f_early, out_px * l.d.cout);
+        } else if (!l.late) {
+            h_early = std::max(h_early, out_px * l.d.cin);
+            f_early = std::max(f_early, out_px * l.d.cout);
+        } else {
+            h_late = std::max(h_late, out_px * l.d.cin);
+            f_late = std::max(f_late, out_px * l.d.cout);
+        }
+    }
+    if (e->layers.back().d.cout != kEmb) return bail("last layer must have 1024 channels");
+    BD_CREATE(cudaMalloc(&e->d_logmel, sizeof(float) * kMel * (static_cast<size_t>(e->S1) * kPatchFrames)));
+    BD_CREATE(cudaMalloc(&e->d_F_early, sizeof(float) * f_early * e->S1));
+    e->H_early_plane_bytes = sizeof(__half) * h_early * e->S1;
+    BD_CREATE(cudaMalloc(&e->d_H_early, sizeof(float) * h_early * e->S1));
+    BD_CREATE(cudaMemset(e->d_H_early, 0, sizeof(float) * h_early * e->S1));
+    BD_CREATE(cudaMalloc(&e->d_F_late, sizeof(float) * f_late * e->S2));
+    e->H_late_plane_bytes = sizeof(__half) * h_late * e->S2;
+    BD_CREATE(cudaMalloc(&e->d_H_late, sizeof(float) * h_late * e->S2));
+    BD_CREATE(cudaMemset(e->d_H_late, 0, sizeof(float) * h_late * e->S2));
+
+    // ---- tensor-core operands: weight planes + TMA descriptors
+    if (e->precision != BD_PRECISION_FP32_SIMT) {
+        const int nsplit = e->precision == BD_PRECISION_FP16X3 ? 3 : 1;
+        for (int L = 1; L < BD_N_LAYERS; ++L) {
+            LayerDev& l = e->layers[L];
+            const size_t nw = static_cast<size_t>(l.d.cout) * l.d.cin;
+            std::vector<__half> hi, lo;
+            split_f16(w->folded + l.d.w, nw, hi, lo);
+            BD_CREATE(cudaMalloc(&l.w_hi, nw * sizeof(__half)));
+            BD_CREATE(cudaMalloc(&l.w_lo, nw * sizeof(__half)));
+            BD_CREATE(cudaMemcpy(l.w_hi, hi.data(), nw * sizeof(__half), cudaMemcpyHostToDevice));
+            BD_CREATE(cudaMemcpy(l.w_lo, lo.data(), nw * sizeof(__half), cudaMemcpyHostToDevice));
+            unsigned char* H = l.late ? e->d_H_late : e->d_H_early;
+            const size_t plane = l.late ? e->H_late_plane_bytes : e->H_early_plane_bytes;
+            const int S = l.late ? e->S2 : e->S1;
+            const int M_max = S * l.h_out * l.w_out;
+            const char* perr = nullptr;
+            cudaError_t pe = pw_gemm_make_plan(&l.plan, reinterpret_cast<__half*>(H), reinterpret_cast<__half*>(H + plane),
+                                               M_max, l.d.cin, l.w_hi, l.w_lo, l.d.cout, nsplit, 0, &perr);
+            if (pe != cudaSuccess) return bail(std::string("pointwise plan for layer ") + std::to_string(L + 1) + ": " +
+                                               (perr ? perr : cudaGetErrorString(pe)));
+        }
+    }
+
+    // ---- host-chunk slots
+    int ns = cfg->n_slots <= 0 ? 2 : std::min(cfg->n_slots, 4);
+    e->slots.resize(ns);
+    for (auto& s : e->slots) {
+        BD_CREATE(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
+        BD_CREATE(cudaEventCreateWithFlags(&s.ev_comp, cudaEventDisableTiming));
+        BD_CREATE(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
+    }
+    BD_CREATE(cudaDeviceSynchronize());
+#undef BD_CREATE
+    *out = e;
+    return 0;
+}
+
+int32_t bd_synchronize(bd_engine* e) {
+    if (!e) return 1;
+    BD_CHECK(e, cudaSetDevice(e->device));
+    BD_CHECK(e, cudaStreamSynchronize(e->s_in));
+    BD_CHECK(e, cudaStreamSynchronize(e->s_compute));
+    BD_CHECK(e, cudaStreamSynchronize(e->s_out));
+    return 0;
+}
+
+int32_t bd_predict_device(bd_engine* e, const float* d_samples, int64_t n, int32_t hop_frames, float* d_act,
+                          float* d_emb, int64_t* n_patches) {
+    if (!e) return 1;
+    if (n < 0 || hop_frames < 1 || hop_frames > kPatchFrames) return fail(e, "bad n / hop_frames");
+    BD_CHECK(e, cudaSetDevice(e->device));
+    int64_t P = 0;
+    frames_for(n, hop_frames, nullptr, nullptr, &P);
+    if (n_patches) *n_patches = P;
+    if (P > 0 && (!d_samples || !d_act)) return fail(e, "null device buffer");
+    if (run_chunk(e, d_samples, n, hop_frames, d_act, d_emb, P)) return 1;
+    BD_CHECK(e, cudaStreamSynchronize(e->s_compute));
+    return 0;
+}
+
+int32_t bd_submit_host(bd_engine* e, int32_t slot, const float* samples, int64_t n, int32_t hop_frames, float* act,
+                       float* emb, int64_t* n_patches) {
+    if (!e) return 1;
+    if (slot < 0 || slot >= static_cast<int>(e->slots.size())) return fail(e, "slot out of range");
+    if (n < 0 || hop_frames < 1 || hop_frames > kPatchFrames) return fail(e, "bad n / hop_frames");
+    BD_CHECK(e, cudaSetDevice(e->device));
+    Slot& s = e->slots[slot];
+    if (s.busy) return fail(e, "slot still in flight: call bd_wait first");
+    int64_t P = 0;
+    frames_for(n, hop_frames, nullptr, nullptr, &P);
+    if (n_patches) *n_patches = P;
+    if (P == 0) return 0;
+    if (!samples || !act) return fail(e, "null host buffer");
+    if (ensure_slot(e, s, n, P)) return 1;
+    BD_CHECK(e, cudaMemcpyAsync(s.d_in, samples, n * sizeof(float), cudaMemcpyHostToDevice, e->s_in));
+    BD_CHECK(e, cudaEventRecord(s.ev_in, e->s_in));
+    BD_CHECK(e, cudaStreamWaitEvent(e->s_compute, s.ev_in, 0));
+    if (run_chunk(e, s.d_in, n, hop_frames, s.d_act, emb ? s.d_emb : nullptr, P)) return 1;
+    BD_CHECK(e, cudaEventRecord(s.ev_comp, e->s_compute));
+    BD_CHECK(e, cudaStreamWaitEvent(e->s_out, s.ev_comp, 0));
+    BD_CHECK(e, cudaMemcpyAsync(act, s.d_act, P * e->n_classes * sizeof(float), cudaMemcpyDeviceToHost, e->s_out));
+    if (emb) BD_CHECK(e, cudaMemcpyAsync(emb, s.d_emb, P * kEmb * sizeof(float), cudaMemcpyDeviceToHost, e->s_out));
+    BD_CHECK(e, cudaEventRecord(s.ev_out, e->s_out));
+    s.busy = true;
+    return 0;
+}
+
+int32_t bd_wait(bd_engine* e, int32_t slot) {
+    if (!e) return 1;
+    if (slot < 0 || slot >= static_cast<int>(e->slots.size())) return fail(e, "slot out of range");
+    Slot& s = e->slots[slot];
+    if (!s.busy) return 0;
+    BD_CHECK(e, cudaSetDevice(e->device));
+    s.busy = false;
+    BD_CHECK(e, cudaEventSynchronize(s.ev_out));
+    return 0;
+}
+
+int32_t bd_predict_host(bd_engine* e, const float* samples, int64_t n, int32_t hop_frames, float* act, float* emb,
+                        int64_t* n_patches) {
+    if (!e) return 1;
+    if (bd_wait(e, 0)) return 1;
+    if (bd_submit_host(e, 0, samples, n, hop_frames, act, emb, n_patches)) return 1;
+    return bd_wait(e, 0);
+}
+
+int32_t bd_profile_device(bd_engine* e, const float* d_samples, int64_t n, int32_t hop_frames, float* ms,
+                          int64_t* launches) {
+    if (!e) return 1;
+    if (n < 0 || hop_frames < 1 || hop_frames > kPatchFrames) return fail(e, "bad n / hop_frames");
+    BD_CHECK(e, cudaSetDevice(e->device));
+    int64_t P = 0;
+    frames_for(n, hop_frames, nullptr, nullptr, &P);
+    for (int i = 0; i < 5; ++i) { ms[i] = 0.f; launches[i] = 0; }
+    if (P == 0) return 0;
+    float* d_act = nullptr;
+    BD_CHECK(e, cudaMalloc(&d_act, P * e->n_classes * sizeof(float)));
+    BD_CHECK(e, cudaStreamSynchronize(e->s_compute));
+    e->profiling = true;
+    e->prof_events.clear();
+    e->prof_cat.clear();
+    cudaEvent_t start;
+    cudaEventCreate(&start);
+    cudaEventRecord(start, e->s_compute);
+    const int64_t before = e->launch_count;
+    const int rc = enqueue_chunk(e, d_samples, n, hop_frames, d_act, nullptr, P, e->s_compute);
+    e->profiling = false;
+    e->launch_count = before;
+    cudaError_t se = cudaStreamSynchronize(e->s_compute);
+    cudaEvent_t prev = start;
+    for (size_t i = 0; i < e->prof_events.size(); ++i) {
+        float t = 0.f;
+        if (rc == 0 && se == cudaSuccess && cudaEventElapsedTime(&t, prev, e->prof_events[i]) == cudaSuccess) {
+            ms[e->prof_cat[i]] += t;
+            launches[e->prof_cat[i]] += 1;
+        }
+        prev = e->prof_events[i];
+    }
+    cudaEventDestroy(start);
+    for (auto ev : e->prof_events) cudaEventDestroy(ev);
+    e->prof_events.clear();
+    e->prof_cat.clear();
+    cudaFree(d_act);
+    if (rc) return rc;
+    BD_CHECK(e, se);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ resampler
+int64_t bd_resample_out_len(int64_t n_frames, int32_t src_rate) {
+    if (n_frames <= 0 || src_rate <= 0) return 0;
+    if (src_rate == 16000) return n_frames;
+    // librosa: int(np.ceil(n * ratio)) with ratio = float(target)/orig (python floats)
+    const double ratio = 16000.0 / static_cast<double>(src_rate);
+    return static_cast<int64_t>(std::ceil(static_cast<double>(n_frames) * ratio));
+}
+
+static int get_resampler(bd_engine* e, int src_rate, bd_engine::Resampler** out) {
+    auto it = e->resamplers.find(src_rate);
+    if (it == e->resamplers.end()) {
+        const int64_t g = gcd64(16000, src_rate);
+        const int up = static_cast<int>(16000 / g), down = static_cast<int>(src_rate / g);
+        if (up > 4096) return fail(e, "unsupported sample-rate ratio (interpolation factor > 4096)");
+        // Kaiser-windowed sinc at the virtual rate up*src_rate: pass-band edge 0.9136*Nyq, stop-band at Nyq of the
+        // lower rate, ~125 dB (soxr "HQ": 20-bit).  See oracle/resample_oracle.py for the same design in numpy.
+        const double f_low = 0.5 * std::min(16000, src_rate);
+        const double fpass = 0.9136 * f_low, fstop = f_low;
+        const double fc = 0.5 * (fpass + fstop);
+        const double att = 125.0;
+        const double beta = 0.1102 * (att - 8.7);
+        const double fs_v = static_cast<double>(up) * src_rate;
+        const double dw = 2.0 * M_PI * (fstop - fpass) / fs_v;
+        int64_t half = static_cast<int64_t>(std::ceil((att - 8.0) / (2.285 * dw) / 2.0));
+        const int tpp = 2 * (static_cast<int>((half + up - 1) / up) + 1);   // taps per phase: covers |t| <= half
+        const int64_t centre = static_cast<int64_t>(tpp / 2) * up;       // h index of t = 0
+        std::vector<float> taps(static_cast<size_t>(tpp) * up, 0.f);
+        const double i0b = bessel_i0(beta);
+        for (int j = 0; j < tpp; ++j) {
+            for (int ph = 0; ph < up; ++ph) {
+                const int64_t idx = static_cast<int64_t>(j) * up + ph;   // prototype index
+                const double t = static_cast<double>(idx - centre);      // in virtual samples
+                const double r = t / static_cast<double>(half);
+                double v = 0.0;
+                if (std::fabs(r) <= 1.0) {
+                    const double arg = 2.0 * fc / fs_v * t;
+                    const double sinc = arg == 0.0 ? 1.0 : std::sin(M_PI * arg) / (M_PI * arg);
+                    const double win = bessel_i0(beta * std::sqrt(1.0 - r * r)) / i0b;
+                    v = 2.0 * fc / fs_v * sinc * win * up;
+                }
+                taps[static_cast<size_t>(j) * up + ph] = static_cast<float>(v);   // layout [tap][phase]
+            }
+        }
+        bd_engine::Resampler r;
+        r.up = up; r.down = down; r.taps_per_phase = tpp; r.d_taps = nullptr;
+        BD_CHECK(e, cudaMalloc(&r.d_taps, taps.size() * sizeof(float)));
+        BD_CHECK(e, cudaMemcpy(r.d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+        it = e->resamplers.emplace(src_rate, r).first;
+    }
+    *out = &it->second;
+    return 0;
+}
+
+int32_t bd_resample_device(bd_engine* e, const void* d_in, int32_t fmt, int32_t channels, int64_t n_frames,
+                           int32_t src_rate, float* d_out, int64_t out_capacity, int64_t* n_out) {
+    if (!e) return 1;
+    if ((fmt != 0 && fmt != 1) || channels < 1 || channels > 8 || src_rate < 1000 || n_frames < 0)
+        return fail(e, "bad resample arguments");
+    BD_CHECK(e, cudaSetDevice(e->device));
+    const int64_t no = bd_resample_out_len(n_frames, src_rate);
+    if (n_out) *n_out = no;
+    if (no > out_capacity) return fail(e, "resample output buffer too small");
+    if (no == 0) return 0;
+    bd_engine::Resampler ident{1, 1, 1, nullptr};
+    bd_engine::Resampler* r = &ident;
+    if (src_rate != 16000 && get_resampler(e, src_rate, &r)) return 1;
+    BD_CHECK(e, launch_resample(d_in, fmt, channels, n_frames, r->up, r->down, r->d_taps, r->taps_per_phase, d_out, no,
+                                e->s_compute));
+    e->launch_count++;
+    BD_CHECK(e, cudaStreamSynchronize(e->s_compute));
+    return 0;
+}
+
+int32_t bd_resample_host(bd_engine* e, const void* in, int32_t fmt, int32_t channels, int64_t n_frames,
+                         int32_t src_rate, float* out, int64_t out_capacity, int64_t* n_out) {
+    if (!e) return 1;
+    if ((fmt != 0 && fmt != 1) || channels < 1 || channels > 8 || src_rate < 1000 || n_frames < 0)
+        return fail(e, "bad resample arguments");
+    BD_CHECK(e, cudaSetDevice(e->device));
+    const int64_t no = bd_resample_out_len(n_frames, src_rate);
+    if (n_out) *n_out = no;
+    if (no > out_capacity) return fail(e, "resample output buffer too small");
+    if (no == 0) return 0;
+    const size_t in_bytes = static_cast<size_t>(n_frames) * channels * (fmt == 0 ? 4 : 2);
+    void* d_in = nullptr;
+    float* d_out = nullptr;
+    BD_CHECK(e, cudaMalloc(&d_in, in_bytes));
+    cudaError_t ce = cudaMalloc(&d_out, no * sizeof(float));
+    if (ce != cudaSuccess) { cudaFree(d_in); BD_CHECK(e, ce); }
+    int rc = 0;
+    ce = cudaMemcpy(d_in, in, in_bytes, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) {
+        rc = bd_resample_device(e, d_in, fmt, channels, n_frames, src_rate, d_out, no, nullptr);
+        if (rc == 0) ce = cudaMemcpy(out, d_out, no * sizeof(float), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (rc) return rc;
+    BD_CHECK(e, ce);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ test hooks
+int32_t bd_debug_logmel(bd_engine* e, const float* samples, int64_t n, int64_t n_frames, float* logmel) {
+    if (!e) return 1;
+    BD_CHECK(e, cudaSetDevice(e->device));
+    if (n_frames <= 0) return 0;
+    float *d_x = nullptr, *d_lm = nullptr;
+    BD_CHECK(e, cudaMalloc(&d_x, std::max<int64_t>(n, 1) * sizeof(float)));
+    BD_CHECK(e, cudaMalloc(&d_lm, n_frames * kMel * sizeof(float)));
+    BD_CHECK(e, cudaMemcpy(d_x, samples, n * sizeof(float), cudaMemcpyHostToDevice));
+    BD_CHECK(e, launch_logmel(d_x, n, 0, static_cast<int>(n_frames), e->d_tab, d_lm, e->num_sms, e->s_compute));
+    e->launch_count++;
+    BD_CHECK(e, cudaStreamSynchronize(e->s_compute));
+    BD_CHECK(e, cudaMemcpy(logmel, d_lm, n_frames * kMel * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaFree(d_x);
+    cudaFree(d_lm);
+    return 0;
+}
+
+int32_t bd_debug_pw_gemm(bd_engine* e, const float* A, const float* W, const float* bias, int32_t M, int32_t N,
+                         int32_t K, int32_t precision, int32_t block_n, float* C) {
+    if (!e) return 1;
+    BD_CHECK(e, cudaSetDevice(e->device));
+    const size_t na = static_cast<size_t>(M) * K, nw = static_cast<size_t>(N) * K, nc = static_cast<size_t>(M) * N;
+    float *dA = nullptr, *dW = nullptr, *dB = nullptr, *dC = nullptr;
+    __half *a_hi = nullptr, *a_lo = nullptr, *w_hi = nullptr, *w_lo = nullptr;
+    BD_CHECK(e, cudaMalloc(&dB, N * sizeof(float)));
+    BD_CHECK(e, cudaMalloc(&dC, nc * sizeof(float)));
+    BD_CHECK(e, cudaMemcpy(dB, bias, N * sizeof(float), cudaMemcpyHostToDevice));
+    int rc = 0;
+    if (precision == BD_PRECISION_FP32_SIMT) {
+        BD_CHECK(e, cudaMalloc(&dA, na * sizeof(float)));
+        BD_CHECK(e, cudaMalloc(&dW, nw * sizeof(float)));
+        BD_CHECK(e, cudaMemcpy(dA, A, na * sizeof(float), cudaMemcpyHostToDevice));
+        BD_CHECK(e, cudaMemcpy(dW, W, nw * sizeof(float), cudaMemcpyHostToDevice));
+        BD_CHECK(e, launch_pw_simt(dA, dW, dB, dC, M, N, K, e->s_compute));
+    } else {
+        BD_CHECK(e, pw_gemm_init_device());
+        std::vector<__half> hi, lo;
+        split_f16(A, na, hi, lo);
+        BD_CHECK(e, cudaMalloc(&a_hi, na * sizeof(__half)));
+        BD_CHECK(e, cudaMalloc(&a_lo, na * sizeof(__half)));
+        BD_CHECK(e, cudaMemcpy(a_hi, hi.data(), na * sizeof(__half), cudaMemcpyHostToDevice));
+        BD_CHECK(e, cudaMemcpy(a_lo, lo.data(), na * sizeof(__half), cudaMemcpyHostToDevice));
+        split_f16(W, nw, hi, lo);
+        BD_CHECK(e, cudaMalloc(&w_hi, nw * sizeof(__half)));
+        BD_CHECK(e, cudaMalloc(&w_lo, nw * sizeof(__half)));
+        BD_CHECK(e, cudaMemcpy(w_hi, hi.data(), nw * sizeof(__half), cudaMemcpyHostToDevice));
+        BD_CHECK(e, cudaMemcpy(w_lo, lo.data(), nw * sizeof(__half), cudaMemcpyHostToDevice));
+        PwGemmPlan plan;
+        const char* perr = nullptr;
+        cudaError_t pe = pw_gemm_make_plan(&plan, a_hi, a_lo, M, K, w_hi, w_lo, N, precision == BD_PRECISION_FP16X3 ? 3 : 1,
+                                           block_n, &perr);
+        if (pe != cudaSuccess) rc = fail(e, std::string("plan: ") + (perr ? perr : cudaGetErrorString(pe)));
+        if (rc == 0) {
+            cudaError_t le = launch_pw_gemm(plan, dB, dC, M, e->num_sms, e->s_compute);
+            if (le != cudaSuccess) rc = fail(e, std::string("launch_pw_gemm: ") + cudaGetErrorString(le));
+        }
+    }
+    e->launch_count++;
+    if (rc == 0) {
+        cudaError_t se = cudaStreamSynchronize(e->s_compute);
+        if (se != cudaSuccess) rc = fail(e, std::string("pw gemm execution: ") + cudaGetErrorString(se));
+    }
+    if (rc == 0) {
+        cudaError_t me = cudaMemcpy(C, dC, nc * sizeof(float), cudaMemcpyDeviceToHost);
+        if (me != cudaSuccess) rc = fail(e, std::string("copy back: ") + cudaGetErrorString(me));
+    }
+    cudaFree(dA); cudaFree(dW); cudaFree(dB); cudaFree(dC);
+    cudaFree(a_hi); cudaFree(a_lo); cudaFree(w_hi); cudaFree(w_lo);
+    return rc;
+}
+
+int32_t bd_debug_stage(bd_engine* e, const float* samples, int64_t n, int32_t hop_frames, int32_t stage, float* out,
+                       int64_t out_capacity, int64_t* n_out) {
+    if (!e) return 1;
+    if (stage < 0 || stage > 2 * (BD_N_LAYERS - 1) + 1) return fail(e, "stage out of range");
+    if (n < 0 || hop_frames < 1 || hop_frames > kPatchFrames) return fail(e, "bad n / hop_frames");
+    BD_CHECK(e, cudaSetDevice(e->device));
+    int64_t P = 0;
+    frames_for(n, hop_frames, nullptr, nullptr, &P);
+    P = std::min<int64_t>(P, e->S1);
+    if (n_out) *n_out = 0;
+    if (P == 0) return 0;
+    float* d_x = nullptr;
+    float* d_act = nullptr;
+    BD_CHECK(e, cudaMalloc(&d_x, std::max<int64_t>(n, 1) * sizeof(float)));
+    BD_CHECK(e, cudaMalloc(&d_act, P * e->n_classes * sizeof(float)));
+    BD_CHECK(e, cudaMemcpy(d_x, samples, n * sizeof(float), cudaMemcpyHostToDevice));
+    int rc = enqueue_chunk(e, d_x, n, hop_frames, d_act, nullptr, P, e->s_compute, stage);
+    if (rc == 0) {
+        cudaError_t se = cudaStreamSynchronize(e->s_compute);
+        if (se != cudaSuccess) rc = fail(e, std::string("stage execution: ") + cudaGetErrorString(se));
+    }
+    if (rc == 0) {
+        int64_t count = 0;
+        const void* src = nullptr;
+        bool planes = false;                // source is hi/lo fp16 planes
+        size_t plane_off = 0;
+        if (stage == 0) {
+            count = (static_cast<int64_t>(P - 1) * hop_frames + kPatchFrames) * kMel;
+            src = e->d_logmel;
+        } else if (stage == 1) {
+            count = P * 48 * 32 * 32;
+            src = e->d_F_early;
+        } else {
+            const int L = stage / 2;        // layer index (0-based): stage 2L = dw out, 2L+1 = pw out
+            const LayerDev& l = e->layers[L];
+            const bool is_dw = (stage % 2) == 0;
+            count = P * l.h_out * l.w_out * (is_dw ? l.d.cin : l.d.cout);
+            if (is_dw) {
+                src = l.late ? e->d_H_late : e->d_H_early;
+                plane_off = l.late ? e->H_late_plane_bytes : e->H_early_plane_bytes;
+                planes = e->precision != BD_PRECISION_FP32_SIMT;
+            } else {
+                src = l.late ? e->d_F_late : e->d_F_early;
+            }
+        }
+        if (count > out_capacity) {
+            rc = fail(e, "debug stage output buffer too small");
+        } else if (!planes) {
+            cudaError_t me = cudaMemcpy(out, src, count * sizeof(float), cudaMemcpyDeviceToHost);
+            if (me != cudaSuccess) rc = fail(e, cudaGetErrorString(me));
+        } else {
+            std::vector<__half> hi(count), lo(count);
+            cudaMemcpy(hi.data(), src, count * sizeof(__half), cudaMemcpyDeviceToHost);
+            if (e->precision == BD_PRECISION_FP16X3)
+                cudaMemcpy(lo.data(), static_cast<const unsigned char*>(src) + plane_off, count * sizeof(__half),
+                           cudaMemcpyDeviceToHost);
+            for (int64_t i = 0; i < count; ++i)
+                out[i] = __half2float(hi[i]) + (e->precision == BD_PRECISION_FP16X3 ? __half2float(lo[i]) : 0.f);
+        }
+        if (rc == 0 && n_out) *n_out = count;
+    }
+    cudaFree(d_x);
+    cudaFree(d_act);
+    return rc;
+}
+
+}  // extern "C"

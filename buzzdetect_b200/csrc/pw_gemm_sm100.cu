@@ -1,0 +1,288 @@
+// Pointwise (1x1) convolution as a tcgen05 GEMM for sm_100a:
+//     C[M,N] = relu(A[M,K] * W[N,K]^T + bias[N])         M = patches*H*W, K = Cin, N = Cout
+// Reference op: Conv2D 1x1 + FusedBatchNormV3 + Relu of _separable_conv (embedders/yamnet/yamnet.py:62-73); BN is
+// folded into W/bias on the host.
+//
+// Precision: the reference computes in float32.  Tensor cores take fp16 operands, so each float32 operand x is
+// carried as two fp16 planes hi = fp16(x), lo = fp16(x - hi).  NSPLIT = 3 issues A_hi*W_hi + A_lo*W_hi + A_hi*W_lo
+// into one float32 TMEM accumulator (error ~2^-22 relative, same as float32 storage); NSPLIT = 1 issues only
+// A_hi*W_hi (error ~2^-11).  See DESIGN.md "precision".
+//
+// Structure (one CTA per SM, persistent over 128 x BN output tiles, warp-specialised):
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor 2-D loads of 128x64 / BNx64 fp16 boxes, SWIZZLE_128B,
+//              STAGES-deep ring guarded by full/empty mbarriers
+//   warp 1   : MMA issuer    -- one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16),
+//              tcgen05.commit releases smem slots and publishes the accumulator
+//   warp 2   : TMEM allocator (2 accumulator stages x BN columns)
+//   warps 4-7: epilogue      -- tcgen05.ld 32x32b -> +bias, ReLU -> float32 stores (row-contiguous 128 B runs)
+#include "bd_common.cuh"
+#include "bd_kernels.cuh"
+
+namespace bd {
+
+namespace {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;                      // 64 fp16 = 128 B = one swizzle row
+constexpr int kGemmThreads = 256;
+constexpr int kSmemBudget = 227 * 1024 - 2048;
+
+template <int BN, int NSPLIT>
+struct GemmCfg {
+    static constexpr int kPlanes = NSPLIT == 1 ? 1 : 2;
+    static constexpr int kATile = kBM * kBK * 2;                 // 16 KB
+    static constexpr int kBTile = BN * kBK * 2;
+    static constexpr int kStageBytes = kPlanes * (kATile + kBTile);
+    static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+    static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+    static constexpr int kTmemCols = 2 * BN;                     // power of two for BN in {64,128,256}
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert(kStages >= 2, "need at least a double buffer");
+    static_assert(kTmemCols >= 32 && kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns");
+};
+
+template <int BN, int NSPLIT>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+               const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K) {
+    using Cfg = GemmCfg<BN, NSPLIT>;
+    constexpr int STAGES = Cfg::kStages;
+    extern __shared__ unsigned char smem_raw[];
+    // SWIZZLE_128B operands need 1024-byte aligned tiles
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+    uint64_t* full_bar = bars;                    // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+    uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = (M + kBM - 1) / kBM, n_tiles = N / BN;
+    const int num_tiles = m_tiles * n_tiles;
+    const int num_kb = (K + kBK - 1) / kBK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a_hi);
+        tma_prefetch_desc(&map_b_hi);
+        if (NSPLIT > 1) {
+            tma_prefetch_desc(&map_a_lo);
+            tma_prefetch_desc(&map_b_lo);
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================================================= TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int m_blk = t / n_tiles, n_blk = t % n_tiles;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char* st = smem + stage * Cfg::kStageBytes;
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    tma_load_2d(st, &map_a_hi, &full_bar[stage], kb * kBK, m_blk * kBM);
+                    if (NSPLIT > 1) tma_load_2d(st + Cfg::kATile, &map_a_lo, &full_bar[stage], kb * kBK, m_blk * kBM);
+                    unsigned char* sb = st + Cfg::kPlanes * Cfg::kATile;
+                    tma_load_2d(sb, &map_b_hi, &full_bar[stage], kb * kBK, n_blk * BN);
+                    if (NSPLIT > 1) tma_load_2d(sb + Cfg::kBTile, &map_b_lo, &full_bar[stage], kb * kBK, n_blk * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================= MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(kBM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
+                    const uint32_t a_lo = a_hi + Cfg::kATile;
+                    const uint32_t b_hi = a_hi + Cfg::kPlanes * Cfg::kATile;
+                    const uint32_t b_lo = b_hi + Cfg::kBTile;
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k) {
+                        const uint32_t koff = static_cast<uint32_t>(k) * 32u;     // 16 fp16 = 32 bytes along K
+                        const uint64_t da_hi = umma_desc_k128(a_hi + koff);
+                        const uint64_t db_hi = umma_desc_k128(b_hi + koff);
+                        umma_f16_ss(d_tmem, da_hi, db_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (NSPLIT > 1) {
+                            const uint64_t da_lo = umma_desc_k128(a_lo + koff);
+                            const uint64_t db_lo = umma_desc_k128(b_lo + koff);
+                            umma_f16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
+                            umma_f16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
+                        }
+                    }
+                    umma_commit(&empty_bar[stage]);          // smem slot reusable once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);                // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================================================= epilogue (warps 4..7 <-> TMEM lane quads)
+        const int q = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int m_blk = t / n_tiles, n_blk = t % n_tiles;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int row = m_blk * kBM + q * 32 + lane;
+            const int n0 = n_blk * BN;
+            float* crow = C + static_cast<long long>(row) * N + n0;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), r);
+                tmem_ld_wait();
+                if (row < M) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
+                        float4 o;
+                        o.x = fmaxf(__uint_as_float(r[j + 0]) + bv.x, 0.f);
+                        o.y = fmaxf(__uint_as_float(r[j + 1]) + bv.y, 0.f);
+                        o.z = fmaxf(__uint_as_float(r[j + 2]) + bv.z, 0.f);
+                        o.w = fmaxf(__uint_as_float(r[j + 3]) + bv.w, 0.f);
+                        *reinterpret_cast<float4*>(crow + c0 + j) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess) {
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        }
+    }
+    return fn;
+}
+
+bool encode_2d_f16(CUtensorMap* map, const void* ptr, int rows, int cols, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) return false;
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <int BN, int NSPLIT>
+cudaError_t set_attr() {
+    return cudaFuncSetAttribute(pw_gemm_kernel<BN, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                GemmCfg<BN, NSPLIT>::kSmemBytes);
+}
+
+template <int BN, int NSPLIT>
+cudaError_t launch_t(const PwGemmPlan& p, const float* bias, float* C, int M, int num_sms, cudaStream_t stream) {
+    const int tiles = ((M + kBM - 1) / kBM) * (p.N / BN);
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    pw_gemm_kernel<BN, NSPLIT><<<grid, kGemmThreads, GemmCfg<BN, NSPLIT>::kSmemBytes, stream>>>(
+        p.a_hi, p.a_lo, p.b_hi, p.b_lo, bias, C, M, p.N, p.K);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t pw_gemm_init_device() {
+    cudaError_t e;
+    if ((e = set_attr<64, 1>()) != cudaSuccess) return e;
+    if ((e = set_attr<128, 1>()) != cudaSuccess) return e;
+    if ((e = set_attr<256, 1>()) != cudaSuccess) return e;
+    if ((e = set_attr<64, 3>()) != cudaSuccess) return e;
+    if ((e = set_attr<128, 3>()) != cudaSuccess) return e;
+    if ((e = set_attr<256, 3>()) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+cudaError_t pw_gemm_make_plan(PwGemmPlan* plan, const __half* a_hi, const __half* a_lo, int M_max, int K,
+                              const __half* b_hi, const __half* b_lo, int N, int nsplit, int block_n,
+                              const char** err) {
+    *err = nullptr;
+    if (nsplit != 1 && nsplit != 3) { *err = "nsplit must be 1 or 3"; return cudaErrorInvalidValue; }
+    if (K % 8 != 0) { *err = "K must be a multiple of 8 (16-byte TMA row stride)"; return cudaErrorInvalidValue; }
+    int bn = block_n;
+    if (bn <= 0) bn = N % 128 == 0 ? 128 : 64;
+    if ((bn != 64 && bn != 128 && bn != 256) || N % bn != 0) { *err = "N must be a multiple of block_n in {64,128,256}"; return cudaErrorInvalidValue; }
+    plan->M_max = M_max; plan->N = N; plan->K = K; plan->block_n = bn; plan->nsplit = nsplit;
+    if (a_lo == nullptr) a_lo = a_hi;
+    if (b_lo == nullptr) b_lo = b_hi;
+    if (!encode_2d_f16(&plan->a_hi, a_hi, M_max, K, kBM) || !encode_2d_f16(&plan->a_lo, a_lo, M_max, K, kBM) ||
+        !encode_2d_f16(&plan->b_hi, b_hi, N, K, bn) || !encode_2d_f16(&plan->b_lo, b_lo, N, K, bn)) {
+        *err = "cuTensorMapEncodeTiled failed";
+        return cudaErrorUnknown;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t launch_pw_gemm(const PwGemmPlan& p, const float* bias, float* C, int M, int num_sms, cudaStream_t stream) {
+    if (M <= 0) return cudaSuccess;
+    if (M > p.M_max) return cudaErrorInvalidValue;
+    if (p.nsplit == 1) {
+        if (p.block_n == 64) return launch_t<64, 1>(p, bias, C, M, num_sms, stream);
+        if (p.block_n == 128) return launch_t<128, 1>(p, bias, C, M, num_sms, stream);
+        return launch_t<256, 1>(p, bias, C, M, num_sms, stream);
+    }
+    if (p.block_n == 64) return launch_t<64, 3>(p, bias, C, M, num_sms, stream);
+    if (p.block_n == 128) return launch_t<128, 3>(p, bias, C, M, num_sms, stream);
+    return launch_t<256, 3>(p, bias, C, M, num_sms, stream);
+}
+
+}  // namespace bd

@@ -1,0 +1,29 @@
+"""B200-native drop-in for the reference's models/model_general_v3/model.py:6-30 (class ModelGeneralV3).
+
+predict(audiosamples) = Dense(13)(embedder.embed(audiosamples)) on raw logits, returned as an object whose
+.numpy() is float32 [n_frames, 13] (what src/write/worker.py:69 consumes).  Embedder and head run in ONE engine
+call: audio goes to the GPU once and only the [n_frames,13] activations come back.
+"""
+try:
+    import src.config as cfg                       # noqa: F401  (inside a buzzdetect checkout)
+    from src.inference.models import BaseModel
+except ImportError:
+    from buzzdetect_b200 import config as cfg     # noqa: F401
+    from buzzdetect_b200.inference.models import BaseModel
+
+
+class ModelGeneralV3(BaseModel):
+    modelname = "model_general_v3"
+    embeddername = 'yamnet_k2'
+    digits_results = 2
+
+    def initialize(self):
+        self.embedder.initialize()
+        self.model = self.embedder.model            # the head lives in the same engine as the embedder
+        if self.model.n_classes != len(self.config['classes']):
+            raise ValueError('head weights and config_model.json disagree on the number of classes')
+
+    def predict(self, audiosamples):
+        from buzzdetect_b200.results import DeviceResults, as_host_f32
+        act = self.model.predict(as_host_f32(audiosamples), self.embedder.hop_frames)
+        return DeviceResults(act)

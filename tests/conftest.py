@@ -1,0 +1,57 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    """The C-ABI library, built in-tree (nvcc cross-compiles without a GPU)."""
+    import __graft_entry__ as g
+    g.build()
+    from buzzdetect_b200 import capi
+    return capi.load_library()
+
+
+@pytest.fixture(scope="session")
+def yamnet_variables():
+    from buzzdetect_b200 import weights as W
+    v, prov = W.resolve_yamnet(verify=True)
+    return v
+
+
+@pytest.fixture(scope="session")
+def head():
+    from buzzdetect_b200 import weights as W
+    return W.load_head()
+
+
+@pytest.fixture(scope="session")
+def mel():
+    from buzzdetect_b200 import weights as W
+    return W.load_mel()
+
+
+@pytest.fixture(scope="session")
+def engines(built_lib, yamnet_variables):
+    """One engine per precision on cuda:0, shared by the GPU tests (small sub-batches to exercise the loops)."""
+    from buzzdetect_b200 import capi
+    cache = {}
+
+    def get(precision="fp16x3", **kw):
+        key = (precision, tuple(sorted(kw.items())))
+        if key not in cache:
+            cache[key] = capi.Engine(device=0, yamnet_variables=yamnet_variables, precision=precision, **kw)
+        return cache[key]
+
+    yield get
+    for e in cache.values():
+        e.close()
