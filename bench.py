@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- audio-hours processed per second through the buzzdetect inference hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path (frontend -> YAMNet MobileNet-v1 -> model_general_v3 head) over one synthetic
+1-hour 16 kHz mono recording per GPU (BASELINE.json configs[1]; 57.6 M float32 samples = 230 MB, larger than the
+126 MB L2, so every step re-reads its audio from HBM).  Files shard across GPUs with no collective (weak scaling).
+
+  value : audio-hours / s with the audio already resident in HBM, timed with CUDA events on the engine's stream
+  e2e   : the same metric through the reference-facing C ABI with HOST (pinned) buffers: per-chunk H2D of the
+          samples and D2H of the activations inside the timed region, chunks pipelined over bd_submit_host/bd_wait
+  roofline     : pointwise (1x1) GEMMs, the dominant kernel class -- algorithmic TFLOP/s against the measured bf16 peak
+  cpu_baseline : the oracle (numpy/torch-CPU restatement of the reference's TensorFlow path) on this box's cores
+  --impl reference : only the CPU oracle is timed (TensorFlow/librosa are not installable here)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SR = 16000
+HOUR_SAMPLES = 3600 * SR
+PATCHES_PER_HOUR = 3750
+HOP_FRAMES = 96
+# algorithmic work per 0.96 s patch (BASELINE.md section 3 / SURVEY.md section 8d)
+PW_FLOP_PER_PATCH = 132_120_576
+DW_BYTES_PER_PATCH = 2_445_312
+FRONTEND_BYTES_PER_PATCH = 86_016
+TOTAL_FLOP_PER_PATCH = 137_289_728
+METRIC = "audio-hours processed/sec (realtime factor) at 1/2/4/8 B200 vs host-CPU ref"
+UNIT = "audio-hours/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus: int):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ----------------------------------------------------------------------------------------------- CPU oracle timing
+def time_oracle(steps: int, warmup: int, chunk_s: float = 199.68, chunks_per_step: int = 1):
+    """The restated reference path on the host cores: reference chunking (199.68 s), all threads."""
+    import numpy as np
+    import torch
+    from buzzdetect_b200 import weights as W
+    from oracle import yamnet_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    variables, prov = W.resolve_yamnet(verify=False)
+    hk, hb = W.load_head()
+    mel = W.load_mel()
+    n = int(round(chunk_s * SR))
+    xs = [O.synth_audio(n, seed=100 + i) for i in range(chunks_per_step)]
+    for _ in range(warmup):
+        O.predict(xs[0], variables, mel, hk, hb, HOP_FRAMES)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for x in xs:
+            O.predict(x, variables, mel, hk, hb, HOP_FRAMES)
+    dt = time.perf_counter() - t0
+    hours = steps * chunks_per_step * chunk_s / 3600.0
+    return hours / dt, dt, cores, f"{steps}x{chunks_per_step} chunk(s) of {chunk_s} s (reference default chunking), " \
+                                  f"oracle = torch-CPU/numpy restatement, weights {prov.split(':')[0]}"
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps, warmup = max(args.steps, 1), max(args.warmup, 1)
+    value, dt, cores, sample = time_oracle(steps, min(warmup, 2))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(warmup, 2), "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "synthetic 16 kHz mono, YAMNet + model_general_v3, hop 1 (configs[1] sampled: "
+                               "one 199.68 s chunk per step)", "chunk_s": 199.68},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "TensorFlow/librosa are absent from this image and the YAMNet blob is absent from the reference "
+                "checkout, so the reference arm is the CPU oracle port (DESIGN.md)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local):
+    import numpy as np
+    import torch
+    import __graft_entry__ as g
+    if rank == 0:
+        g.build()
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    from buzzdetect_b200 import capi
+    from oracle import yamnet_oracle as O            # synthetic audio generator + cpu_baseline only
+
+    dev = local if use_dist else 0
+    torch.cuda.set_device(dev)
+    eng = capi.Engine(device=dev, precision=args.precision, early_patches=args.early, late_patches=args.late,
+                      n_slots=3)
+    hours_per_step = args.hours
+    n = int(round(hours_per_step * HOUR_SAMPLES))
+    # one hour of synthetic audio: 60 s of the oracle's generator tiled with per-rank seed (host I/O is not measured)
+    base = O.synth_audio(60 * SR, seed=1000 + rank)
+    host = torch.empty(n, dtype=torch.float32).pin_memory()
+    hv = host.numpy()
+    for off in range(0, n, base.size):
+        m = min(base.size, n - off)
+        hv[off:off + m] = base[:m]
+    _, _, P = capi.frames_for(n, HOP_FRAMES)
+    d_x = host.cuda(non_blocking=False)
+    d_act = torch.empty((P, eng.n_classes), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput ("value")
+    for _ in range(max(args.warmup, 3)):
+        eng.predict_device_ptr(d_x.data_ptr(), n, HOP_FRAMES, d_act.data_ptr())
+    if use_dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count
+    ms = eng.bench_device_ptr(d_x.data_ptr(), n, HOP_FRAMES, d_act.data_ptr(), args.steps)
+    torch.cuda.synchronize()
+    launches = eng.launch_count - l0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if use_dist:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * hours_per_step * args.steps / (ms_max / 1000.0)
+
+    # ---------------- end to end through the C ABI with host buffers
+    chunk_n = int(round(args.chunk_s * SR))
+    chunks = [(o, min(chunk_n, n - o)) for o in range(0, n, chunk_n)]
+    outs = []
+    for (o, m) in chunks:
+        _, _, p = capi.frames_for(m, HOP_FRAMES)
+        outs.append(torch.empty((p, eng.n_classes), dtype=torch.float32).pin_memory())
+    n_slots = 3
+
+    def e2e_pass():
+        for i, (o, m) in enumerate(chunks):
+            s = i % n_slots
+            eng.wait(s)
+            eng.submit_ptr(s, host.data_ptr() + 4 * o, m, HOP_FRAMES, outs[i].data_ptr())
+        for s in range(n_slots):
+            eng.wait(s)
+
+    for _ in range(max(args.warmup, 3)):
+        e2e_pass()
+    eng.synchronize()
+    if use_dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_pass()
+    eng.synchronize()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if use_dist:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * hours_per_step * args.steps / float(t.item())
+    d2h_bytes = sum(o.numel() * 4 for o in outs)
+
+    # ---------------- per-stage device times (one extra un-graphed pass, events around every launch)
+    prof = eng.profile_device_ptr(d_x.data_ptr(), n, HOP_FRAMES)
+    peaks = measured_peaks()
+    pw_ms = prof["pointwise"]["ms"]
+    pw_l = max(prof["pointwise"]["launches"], 1)
+    pw_tflops = PW_FLOP_PER_PATCH * P / (pw_ms / 1000.0) / 1e12 if pw_ms > 0 else 0.0
+    mma_factor = {"fp16x3": 3, "fp16": 1, "fp32": 0}[args.precision]
+    stages = {}
+    for name, bytes_pp in (("frontend", FRONTEND_BYTES_PER_PATCH), ("depthwise", DW_BYTES_PER_PATCH)):
+        m = prof[name]["ms"]
+        gbs = bytes_pp * P / (m / 1000.0) / 1e9 if m > 0 else 0.0
+        stages[name] = {"ms": m, "launches": prof[name]["launches"], "achieved_gbs": gbs,
+                        "frac_hbm": gbs / peaks["hbm_gbs"]}
+    stages["pointwise"] = {"ms": pw_ms, "launches": prof["pointwise"]["launches"], "achieved_tflops": pw_tflops,
+                           "executed_mma_tflops": pw_tflops * mma_factor}
+    stages["conv1"] = prof["conv1"]
+    stages["pool_head"] = prof["pool_head"]
+    total_prof_ms = sum(prof[k]["ms"] for k in ("frontend", "conv1", "depthwise", "pointwise", "pool_head"))
+    # per-layer view: algorithmic bytes (fp32 in + out) for depthwise, flops for pointwise
+    from buzzdetect_b200.weights import LAYERS
+    per_layer = {}
+    for i, (kind, stride, cin, cout, H, W) in enumerate(LAYERS[1:]):
+        v = prof["layers"][f"L{i + 2}"]
+        ho, wo = H // stride, W // stride
+        dw_bytes = (H * W * cin + ho * wo * cin) * 4 * P
+        pw_flop = 2.0 * ho * wo * cin * cout * P
+        pw_bytes = (ho * wo * cin + ho * wo * cout) * 4 * P
+        per_layer[f"L{i + 2}"] = {
+            "dw_ms": round(v["dw_ms"], 4), "dw_gbs": round(dw_bytes / max(v["dw_ms"], 1e-9) / 1e6, 1),
+            "pw_ms": round(v["pw_ms"], 4), "pw_tflops": round(pw_flop / max(v["pw_ms"], 1e-9) / 1e9, 1),
+            "pw_gbs": round(pw_bytes / max(v["pw_ms"], 1e-9) / 1e6, 1), "K": cin, "N": cout, "M": ho * wo * P}
+    roofline = {
+        "bound": "tensor", "kernel": "pw_gemm_kernel (13 pointwise 1x1 convs)",
+        "achieved": pw_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+        "frac": pw_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
+        "peak_source": peaks["source"] + " bf16 sustained (kernel timed inside a long step)",
+        "flop_per_launch": PW_FLOP_PER_PATCH * P / pw_l, "avg_launch_ms": pw_ms / pw_l,
+        "share_of_step": pw_ms / total_prof_ms if total_prof_ms > 0 else None,
+        "executed_mma_factor": mma_factor,
+    }
+
+    if rank == 0:
+        cpu_v, cpu_dt, cores, sample = time_oracle(steps=2, warmup=1) if (world == 1 and not args.no_cpu) else (None,) * 4
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision != "fp16" else "f16",
+            "data": "synthetic",
+            "config": {"workload": f"synthetic {hours_per_step:g}-hour 16 kHz mono recording per GPU, YAMNet + "
+                                   "model_general_v3, hop 1 (BASELINE configs[1])",
+                       "patches_per_step_per_gpu": P, "pointwise_precision": args.precision,
+                       "weights": eng.weights_provenance.split(":")[0],
+                       "l2": "input (230 MB/step) larger than L2; no explicit flush", "e2e_chunk_s": args.chunk_s,
+                       "early_patches": args.early, "late_patches": args.late, "sharding": "one file per GPU, no collective"},
+            "realtime_factor": value * 3600.0,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": d2h_bytes,
+                    "chunks_per_step": len(chunks), "slots": n_slots},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "stages": stages,
+            "layers": per_layer,
+            "whole_path_tflops": TOTAL_FLOP_PER_PATCH * P * world * args.steps / (ms_max / 1000.0) / 1e12,
+        }
+        if cpu_v is not None:
+            line["cpu_baseline"] = {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if use_dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("BUZZ_B200_PRECISION", "fp16x3"),
+                    choices=["fp16x3", "fp16", "fp32"])
+    ap.add_argument("--hours", type=float, default=1.0, help="audio hours per step per GPU")
+    ap.add_argument("--chunk-s", dest="chunk_s", type=float, default=1198.08,
+                    help="chunk length of the end-to-end (host buffer) leg; multiple of 0.96 s")
+    ap.add_argument("--early", type=int, default=0)
+    ap.add_argument("--late", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank, world, local = dist_setup(args.gpus)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local)
+
+
+if __name__ == "__main__":
+    main()

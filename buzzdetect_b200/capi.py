@@ -61,6 +61,7 @@ SIGNATURES = {
     "bd_synchronize": (C.c_int32, [C.c_void_p]),
     "bd_profile_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, _f32p, _i64p]),
     "bd_launch_count": (C.c_int64, [C.c_void_p]),
+    "bd_bench_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, _f32p]),
     "bd_resample_out_len": (C.c_int64, [C.c_int64, C.c_int32]),
     "bd_resample_host": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p,
                                      C.c_int64, _i64p]),
@@ -234,11 +235,25 @@ class Engine:
                     "bd_predict_device")
         return npat.value
 
+    def bench_device_ptr(self, d_samples: int, n: int, hop_frames: int, d_act: int, steps: int) -> float:
+        """milliseconds (CUDA events on the engine's compute stream) for `steps` passes over one resident chunk."""
+        ms = C.c_float()
+        self._check(self._lib.bd_bench_device(self._h, d_samples, n, hop_frames, d_act, steps, C.byref(ms)),
+                    "bd_bench_device")
+        return float(ms.value)
+
     def profile_device_ptr(self, d_samples: int, n: int, hop_frames: int = 96) -> dict:
-        ms = (C.c_float * 5)()
-        cnt = (C.c_int64 * 5)()
+        ms = (C.c_float * 29)()
+        cnt = (C.c_int64 * 29)()
         self._check(self._lib.bd_profile_device(self._h, d_samples, n, hop_frames, ms, cnt), "bd_profile_device")
-        return {s: {"ms": float(ms[i]), "launches": int(cnt[i])} for i, s in enumerate(STAGES)}
+        groups = {"frontend": [0], "conv1": [1], "depthwise": list(range(2, 15)), "pointwise": list(range(15, 28)),
+                  "pool_head": [28]}
+        out = {s: {"ms": float(sum(ms[i] for i in idx)), "launches": int(sum(cnt[i] for i in idx))}
+               for s, idx in groups.items()}
+        out["layers"] = {f"L{i + 2}": {"dw_ms": float(ms[2 + i]), "pw_ms": float(ms[15 + i]),
+                                       "dw_launches": int(cnt[2 + i]), "pw_launches": int(cnt[15 + i])}
+                         for i in range(13)}
+        return out
 
     # ------------------------------------------------------------------ resampler
     def resample(self, samples: np.ndarray, src_rate: int) -> np.ndarray:

@@ -57,13 +57,18 @@ cudaError_t launch_pool_head(const float* y, int P, int rows_per_patch, const fl
 struct PwGemmPlan {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     int M_max, N, K, block_n, nsplit;
+    float out_scale;   // accumulators are multiplied by this before the bias (weights are stored pre-scaled by 1/out_scale)
 };
 cudaError_t pw_gemm_init_device();
 // Build TMA descriptors for A planes [M_max, K] (row stride lda halfs) and weight planes [N, K].
 // block_n: 64/128/256, or 0 to choose automatically.
 cudaError_t pw_gemm_make_plan(PwGemmPlan* plan, const __half* a_hi, const __half* a_lo, int M_max, int K,
                               const __half* b_hi, const __half* b_lo, int N, int nsplit, int block_n,
-                              const char** err);
+                              float out_scale, const char** err);
+// Split float32 weights into fp16 hi/lo planes after scaling by a power of two chosen so that max|w| lands in
+// [512,1024): the lo plane then stays in fp16's NORMAL range (unscaled 1x1 weights are ~0.05, their lo parts would be
+// subnormal and carry only ~1e-6 relative precision).  Returns the inverse scale for PwGemmPlan::out_scale.
+float split_weights_f16(const float* w, size_t n, __half* hi, __half* lo);
 cudaError_t launch_pw_gemm(const PwGemmPlan& plan, const float* bias, float* C, int M, int num_sms,
                            cudaStream_t stream);
 

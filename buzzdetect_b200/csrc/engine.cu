@@ -58,7 +58,7 @@ struct GraphKey {
 
 struct bd_engine {
     int device = 0, num_sms = 148, precision = BD_PRECISION_FP16X3;
-    int S1 = 64, S2 = 512, n_classes = 13;
+    int S1 = 1024, S2 = 4096, n_classes = 13;
     bool use_graph = true;
     cudaStream_t s_compute = nullptr, s_in = nullptr, s_out = nullptr;
     float* d_folded = nullptr;
@@ -125,7 +125,8 @@ void frames_for(int64_t n, int hop_frames, int64_t* n_padded, int64_t* n_frames,
 }
 
 // ------------------------------------------------------------------------------------------ profiling hooks
-enum Cat { CAT_FRONTEND = 0, CAT_CONV1 = 1, CAT_DW = 2, CAT_PW = 3, CAT_POOL = 4 };
+// profiling categories: 0 frontend, 1 conv1, 2+i depthwise of layer i+2, 15+i pointwise of layer i+2, 28 pool+head
+enum Cat { CAT_FRONTEND = 0, CAT_CONV1 = 1, CAT_DW = 2, CAT_PW = 15, CAT_POOL = 28, CAT_COUNT = 29 };
 
 void mark(bd_engine* e, int cat, cudaStream_t st) {
     e->launch_count++;
@@ -146,16 +147,19 @@ int enqueue_chunk(bd_engine* e, const float* x, int64_t n, int hop_frames, float
     const int dw_mode = prec == BD_PRECISION_FP32_SIMT ? 0 : (prec == BD_PRECISION_FP16X1 ? 1 : 2);
     for (int64_t big = 0; big < P; big += e->S2) {
         const int nb = static_cast<int>(std::min<int64_t>(e->S2, P - big));
+        // ---------------- frontend: log-mel of the whole late batch in one launch (24.6 KB per patch)
+        {
+            const int n_fr = (nb - 1) * hop_frames + kPatchFrames;
+            BD_CHECK(e, launch_logmel(x, n, big * hop_frames, n_fr, e->d_tab, e->d_logmel, e->num_sms, st));
+            mark(e, CAT_FRONTEND, st);
+            if (stop_stage == 0) return 0;
+        }
         // ---------------- early phase
         for (int small = 0; small < nb; small += e->S1) {
             const int ns = std::min(e->S1, nb - small);
-            const int64_t p0 = big + small;
-            const int n_fr = (ns - 1) * hop_frames + kPatchFrames;
-            BD_CHECK(e, launch_logmel(x, n, p0 * hop_frames, n_fr, e->d_tab, e->d_logmel, e->num_sms, st));
-            mark(e, CAT_FRONTEND, st);
-            if (stop_stage == 0) return 0;
             const LayerDev& l1 = e->layers[0];
-            BD_CHECK(e, launch_conv1(e->d_logmel, hop_frames, ns, l1.w, l1.b, e->d_F_early, st));
+            BD_CHECK(e, launch_conv1(e->d_logmel + static_cast<int64_t>(small) * hop_frames * kMel, hop_frames, ns, l1.w,
+                                     l1.b, e->d_F_early, st));
             mark(e, CAT_CONV1, st);
             if (stop_stage == 1) return 0;
             for (int L = 1; L < BD_N_LAYERS; ++L) {
@@ -169,7 +173,7 @@ int enqueue_chunk(bd_engine* e, const float* x, int64_t n, int hop_frames, float
                 __half* olo = reinterpret_cast<__half*>(H + plane) + row_off * l.d.cin;
                 BD_CHECK(e, launch_depthwise(e->d_F_early, ns, l.d.h_in, l.d.w_in, l.d.cin, l.d.stride, l.dw_w, l.dw_b,
                                              dw_mode, o32, ohi, olo, st));
-                mark(e, CAT_DW, st);
+                mark(e, CAT_DW + L - 1, st);
                 if (stop_stage == 2 * L) return 0;
                 if (to_late) break;
                 const int M = ns * l.h_out * l.w_out;
@@ -179,7 +183,7 @@ int enqueue_chunk(bd_engine* e, const float* x, int64_t n, int hop_frames, float
                 } else {
                     BD_CHECK(e, launch_pw_gemm(l.plan, l.b, e->d_F_early, M, e->num_sms, st));
                 }
-                mark(e, CAT_PW, st);
+                mark(e, CAT_PW + L - 1, st);
                 if (stop_stage == 2 * L + 1) return 0;
             }
         }
@@ -193,7 +197,7 @@ int enqueue_chunk(bd_engine* e, const float* x, int64_t n, int hop_frames, float
                                              dw_mode, reinterpret_cast<float*>(e->d_H_late),
                                              reinterpret_cast<__half*>(e->d_H_late),
                                              reinterpret_cast<__half*>(e->d_H_late + e->H_late_plane_bytes), st));
-                mark(e, CAT_DW, st);
+                mark(e, CAT_DW + L - 1, st);
                 if (stop_stage == 2 * L) return 0;
             }
             const int M = nb * l.h_out * l.w_out;
@@ -203,7 +207,7 @@ int enqueue_chunk(bd_engine* e, const float* x, int64_t n, int hop_frames, float
             } else {
                 BD_CHECK(e, launch_pw_gemm(l.plan, l.b, e->d_F_late, M, e->num_sms, st));
             }
-            mark(e, CAT_PW, st);
+            mark(e, CAT_PW + L - 1, st);
             if (stop_stage == 2 * L + 1) return 0;
         }
         const LayerDev& last = e->layers[BD_N_LAYERS - 1];
@@ -358,8 +362,8 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
     e->device = cfg->device;
     e->num_sms = prop.multiProcessorCount;
     e->precision = cfg->precision;
-    e->S1 = cfg->early_patches > 0 ? cfg->early_patches : 64;
-    e->S2 = cfg->late_patches > 0 ? cfg->late_patches : 512;
+    e->S1 = cfg->early_patches > 0 ? cfg->early_patches : 1024;
+    e->S2 = cfg->late_patches > 0 ? cfg->late_patches : 4096;
     e->S2 = std::max(e->S1, (e->S2 / e->S1) * e->S1);           // late batch = whole number of early batches
     e->use_graph = cfg->use_graph != 0;
     e->n_classes = w->n_classes;
@@ -432,7 +436,7 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
         }
     }
     if (e->layers.back().d.cout != kEmb) return bail("last layer must have 1024 channels");
-    BD_CREATE(cudaMalloc(&e->d_logmel, sizeof(float) * kMel * (static_cast<size_t>(e->S1) * kPatchFrames)));
+    BD_CREATE(cudaMalloc(&e->d_logmel, sizeof(float) * kMel * (static_cast<size_t>(e->S2) * kPatchFrames)));
     BD_CREATE(cudaMalloc(&e->d_F_early, sizeof(float) * f_early * e->S1));
     e->H_early_plane_bytes = sizeof(__half) * h_early * e->S1;
     BD_CREATE(cudaMalloc(&e->d_H_early, sizeof(float) * h_early * e->S1));
@@ -448,8 +452,8 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
         for (int L = 1; L < BD_N_LAYERS; ++L) {
             LayerDev& l = e->layers[L];
             const size_t nw = static_cast<size_t>(l.d.cout) * l.d.cin;
-            std::vector<__half> hi, lo;
-            split_f16(w->folded + l.d.w, nw, hi, lo);
+            std::vector<__half> hi(nw), lo(nw);
+            const float out_scale = split_weights_f16(w->folded + l.d.w, nw, hi.data(), lo.data());
             BD_CREATE(cudaMalloc(&l.w_hi, nw * sizeof(__half)));
             BD_CREATE(cudaMalloc(&l.w_lo, nw * sizeof(__half)));
             BD_CREATE(cudaMemcpy(l.w_hi, hi.data(), nw * sizeof(__half), cudaMemcpyHostToDevice));
@@ -460,7 +464,7 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
             const int M_max = S * l.h_out * l.w_out;
             const char* perr = nullptr;
             cudaError_t pe = pw_gemm_make_plan(&l.plan, reinterpret_cast<__half*>(H), reinterpret_cast<__half*>(H + plane),
-                                               M_max, l.d.cin, l.w_hi, l.w_lo, l.d.cout, nsplit, 0, &perr);
+                                               M_max, l.d.cin, l.w_hi, l.w_lo, l.d.cout, nsplit, 0, out_scale, &perr);
             if (pe != cudaSuccess) return bail(std::string("pointwise plan for layer ") + std::to_string(L + 1) + ": " +
                                                (perr ? perr : cudaGetErrorString(pe)));
         }
@@ -556,7 +560,7 @@ int32_t bd_profile_device(bd_engine* e, const float* d_samples, int64_t n, int32
     BD_CHECK(e, cudaSetDevice(e->device));
     int64_t P = 0;
     frames_for(n, hop_frames, nullptr, nullptr, &P);
-    for (int i = 0; i < 5; ++i) { ms[i] = 0.f; launches[i] = 0; }
+    for (int i = 0; i < CAT_COUNT; ++i) { ms[i] = 0.f; launches[i] = 0; }
     if (P == 0) return 0;
     float* d_act = nullptr;
     BD_CHECK(e, cudaMalloc(&d_act, P * e->n_classes * sizeof(float)));
@@ -588,6 +592,33 @@ int32_t bd_profile_device(bd_engine* e, const float* d_samples, int64_t n, int32
     cudaFree(d_act);
     if (rc) return rc;
     BD_CHECK(e, se);
+    return 0;
+}
+
+int32_t bd_bench_device(bd_engine* e, const float* d_samples, int64_t n, int32_t hop_frames, float* d_act,
+                        int32_t steps, float* ms_total) {
+    if (!e) return 1;
+    if (n < 0 || hop_frames < 1 || hop_frames > kPatchFrames || steps < 1) return fail(e, "bad arguments");
+    BD_CHECK(e, cudaSetDevice(e->device));
+    int64_t P = 0;
+    frames_for(n, hop_frames, nullptr, nullptr, &P);
+    if (P == 0 || !d_samples || !d_act) return fail(e, "nothing to run");
+    cudaEvent_t e0, e1;
+    BD_CHECK(e, cudaEventCreate(&e0));
+    BD_CHECK(e, cudaEventCreate(&e1));
+    BD_CHECK(e, cudaStreamSynchronize(e->s_compute));
+    BD_CHECK(e, cudaEventRecord(e0, e->s_compute));
+    int rc = 0;
+    for (int i = 0; i < steps && rc == 0; ++i) rc = run_chunk(e, d_samples, n, hop_frames, d_act, nullptr, P);
+    cudaEventRecord(e1, e->s_compute);
+    cudaError_t se = cudaStreamSynchronize(e->s_compute);
+    float ms = 0.f;
+    if (rc == 0 && se == cudaSuccess) se = cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc) return rc;
+    BD_CHECK(e, se);
+    if (ms_total) *ms_total = ms;
     return 0;
 }
 
@@ -737,7 +768,8 @@ int32_t bd_debug_pw_gemm(bd_engine* e, const float* A, const float* W, const flo
         BD_CHECK(e, cudaMalloc(&a_lo, na * sizeof(__half)));
         BD_CHECK(e, cudaMemcpy(a_hi, hi.data(), na * sizeof(__half), cudaMemcpyHostToDevice));
         BD_CHECK(e, cudaMemcpy(a_lo, lo.data(), na * sizeof(__half), cudaMemcpyHostToDevice));
-        split_f16(W, nw, hi, lo);
+        hi.resize(nw); lo.resize(nw);
+        const float out_scale = split_weights_f16(W, nw, hi.data(), lo.data());
         BD_CHECK(e, cudaMalloc(&w_hi, nw * sizeof(__half)));
         BD_CHECK(e, cudaMalloc(&w_lo, nw * sizeof(__half)));
         BD_CHECK(e, cudaMemcpy(w_hi, hi.data(), nw * sizeof(__half), cudaMemcpyHostToDevice));
@@ -745,7 +777,7 @@ int32_t bd_debug_pw_gemm(bd_engine* e, const float* A, const float* W, const flo
         PwGemmPlan plan;
         const char* perr = nullptr;
         cudaError_t pe = pw_gemm_make_plan(&plan, a_hi, a_lo, M, K, w_hi, w_lo, N, precision == BD_PRECISION_FP16X3 ? 3 : 1,
-                                           block_n, &perr);
+                                           block_n, out_scale, &perr);
         if (pe != cudaSuccess) rc = fail(e, std::string("plan: ") + (perr ? perr : cudaGetErrorString(pe)));
         if (rc == 0) {
             cudaError_t le = launch_pw_gemm(plan, dB, dC, M, e->num_sms, e->s_compute);

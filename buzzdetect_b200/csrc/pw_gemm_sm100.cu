@@ -15,6 +15,8 @@
 //              tcgen05.commit releases smem slots and publishes the accumulator
 //   warp 2   : TMEM allocator (2 accumulator stages x BN columns)
 //   warps 4-7: epilogue      -- tcgen05.ld 32x32b -> +bias, ReLU -> float32 stores (row-contiguous 128 B runs)
+#include <cmath>
+
 #include "bd_common.cuh"
 #include "bd_kernels.cuh"
 
@@ -45,7 +47,7 @@ template <int BN, int NSPLIT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-               const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K) {
+               const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K, float out_scale) {
     using Cfg = GemmCfg<BN, NSPLIT>;
     constexpr int STAGES = Cfg::kStages;
     extern __shared__ unsigned char smem_raw[];
@@ -170,10 +172,10 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     for (int j = 0; j < 32; j += 4) {
                         const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
                         float4 o;
-                        o.x = fmaxf(__uint_as_float(r[j + 0]) + bv.x, 0.f);
-                        o.y = fmaxf(__uint_as_float(r[j + 1]) + bv.y, 0.f);
-                        o.z = fmaxf(__uint_as_float(r[j + 2]) + bv.z, 0.f);
-                        o.w = fmaxf(__uint_as_float(r[j + 3]) + bv.w, 0.f);
+                        o.x = fmaxf(fmaf(__uint_as_float(r[j + 0]), out_scale, bv.x), 0.f);
+                        o.y = fmaxf(fmaf(__uint_as_float(r[j + 1]), out_scale, bv.y), 0.f);
+                        o.z = fmaxf(fmaf(__uint_as_float(r[j + 2]), out_scale, bv.z), 0.f);
+                        o.w = fmaxf(fmaf(__uint_as_float(r[j + 3]), out_scale, bv.w), 0.f);
                         *reinterpret_cast<float4*>(crow + c0 + j) = o;
                     }
                 }
@@ -235,11 +237,29 @@ cudaError_t launch_t(const PwGemmPlan& p, const float* bias, float* C, int M, in
     const int tiles = ((M + kBM - 1) / kBM) * (p.N / BN);
     const int grid = tiles < num_sms ? tiles : num_sms;
     pw_gemm_kernel<BN, NSPLIT><<<grid, kGemmThreads, GemmCfg<BN, NSPLIT>::kSmemBytes, stream>>>(
-        p.a_hi, p.a_lo, p.b_hi, p.b_lo, bias, C, M, p.N, p.K);
+        p.a_hi, p.a_lo, p.b_hi, p.b_lo, bias, C, M, p.N, p.K, p.out_scale);
     return cudaGetLastError();
 }
 
 }  // namespace
+
+float split_weights_f16(const float* w, size_t n, __half* hi, __half* lo) {
+    float mx = 0.f;
+    for (size_t i = 0; i < n; ++i) mx = fmaxf(mx, fabsf(w[i]));
+    int ex = 0;
+    float scale = 1.f;
+    if (mx > 0.f && std::isfinite(mx)) {
+        std::frexp(mx, &ex);                  // mx = f * 2^ex, f in [0.5,1)
+        scale = std::ldexp(1.0f, 10 - ex);    // mx*scale in [512,1024)
+    }
+    for (size_t i = 0; i < n; ++i) {
+        const float v = w[i] * scale;         // exact (power of two)
+        const __half h = __float2half_rn(v);
+        hi[i] = h;
+        lo[i] = __float2half_rn(v - __half2float(h));
+    }
+    return 1.0f / scale;
+}
 
 cudaError_t pw_gemm_init_device() {
     cudaError_t e;
@@ -254,14 +274,14 @@ cudaError_t pw_gemm_init_device() {
 
 cudaError_t pw_gemm_make_plan(PwGemmPlan* plan, const __half* a_hi, const __half* a_lo, int M_max, int K,
                               const __half* b_hi, const __half* b_lo, int N, int nsplit, int block_n,
-                              const char** err) {
+                              float out_scale, const char** err) {
     *err = nullptr;
     if (nsplit != 1 && nsplit != 3) { *err = "nsplit must be 1 or 3"; return cudaErrorInvalidValue; }
     if (K % 8 != 0) { *err = "K must be a multiple of 8 (16-byte TMA row stride)"; return cudaErrorInvalidValue; }
     int bn = block_n;
     if (bn <= 0) bn = N % 128 == 0 ? 128 : 64;
     if ((bn != 64 && bn != 128 && bn != 256) || N % bn != 0) { *err = "N must be a multiple of block_n in {64,128,256}"; return cudaErrorInvalidValue; }
-    plan->M_max = M_max; plan->N = N; plan->K = K; plan->block_n = bn; plan->nsplit = nsplit;
+    plan->M_max = M_max; plan->N = N; plan->K = K; plan->block_n = bn; plan->nsplit = nsplit; plan->out_scale = out_scale;
     if (a_lo == nullptr) a_lo = a_hi;
     if (b_lo == nullptr) b_lo = b_hi;
     if (!encode_2d_f16(&plan->a_hi, a_hi, M_max, K, kBM) || !encode_2d_f16(&plan->a_lo, a_lo, M_max, K, kBM) ||

@@ -129,6 +129,7 @@ def load_yamnet_blob(path: str, verify: bool = True) -> dict:
 # tools/calibrate_synthetic.py on oracle.synth_audio(16000*20, seed=123) with SYNTH_SEED below.  They only
 # keep the random network's activations O(1) from layer to layer, like a freshly BN-calibrated net.
 SYNTH_SEED = 20251018
+SYNTH_EMB_SCALE = 0.125
 SYNTH_CALIB: list[tuple[float, float]] = []   # filled below from assets/synth_calibration.json if present
 _calib_path = os.path.join(ASSETS, "synth_calibration.json")
 if os.path.exists(_calib_path):
@@ -158,9 +159,17 @@ def synthetic_yamnet(seed: int = SYNTH_SEED, calib: list | None = None, upto: in
     def bn(prefix, w_sum, c):
         nonlocal stage
         mu_in, v = calib[stage] if stage < len(calib) else (0.0, 1.0)
-        out[prefix + "/beta"] = (0.1 + 0.3 * rng.standard_normal(c)).astype(np.float32)
+        beta = 0.1 + 0.3 * rng.standard_normal(c)
+        var = v * rng.uniform(0.5, 2.0, c)
+        if stage == 26:
+            # last stage: shrink the embeddings so that the REAL model_general_v3 head produces logits in the range
+            # the reference documents (about -6 .. +1.5, models/model_general_v3/tests/metrics.csv); the absolute
+            # 1e-3 activation tolerance is then tested at a realistic scale.
+            beta = beta * SYNTH_EMB_SCALE
+            var = var / SYNTH_EMB_SCALE ** 2
+        out[prefix + "/beta"] = beta.astype(np.float32)
         out[prefix + "/moving_mean"] = (mu_in * w_sum).astype(np.float32)
-        out[prefix + "/moving_variance"] = (v * rng.uniform(0.5, 2.0, c)).astype(np.float32)
+        out[prefix + "/moving_variance"] = var.astype(np.float32)
         stage += 1
 
     for (kind, s, cin, cout, H, W), nm in zip(LAYERS, names):

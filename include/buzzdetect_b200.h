@@ -89,11 +89,17 @@ int32_t bd_submit_host(bd_engine* e, int32_t slot, const float* samples, int64_t
 int32_t bd_wait(bd_engine* e, int32_t slot);
 int32_t bd_synchronize(bd_engine* e);
 
-/* Per-stage device time of one un-graphed pass over device-resident audio.
- * ms[5] / launches[5]: 0 frontend, 1 conv1, 2 depthwise, 3 pointwise, 4 pool+head. */
+/* Per-kernel-class device time of one un-graphed pass over device-resident audio (CUDA events around every
+ * launch).  ms[BD_PROFILE_SLOTS] / launches[BD_PROFILE_SLOTS]: 0 frontend, 1 conv1, 2+i depthwise of layer i+2,
+ * 15+i pointwise of layer i+2 (i = 0..12), 28 pool+head. */
+#define BD_PROFILE_SLOTS 29
 int32_t bd_profile_device(bd_engine* e, const float* d_samples, int64_t n, int32_t hop_frames, float* ms,
                           int64_t* launches);
 int64_t bd_launch_count(const bd_engine* e);     /* kernels launched (or replayed from graphs) so far */
+/* `steps` back-to-back passes over the same device-resident chunk, timed with CUDA events recorded on the
+ * engine's own compute stream (torch.cuda.Event would only see torch's current stream). */
+int32_t bd_bench_device(bd_engine* e, const float* d_samples, int64_t n, int32_t hop_frames, float* d_act,
+                        int32_t steps, float* ms_total);
 
 /* Downmix + polyphase resample of one decoded chunk to 16 kHz (src/stream/worker.py:116-128).
  * in: interleaved [n_frames, channels], fmt 0 = float32, 1 = int16 (scaled by 1/32768 like soundfile).

@@ -17,11 +17,15 @@ REPORT = {}
 
 
 def _report(key, val):
-    REPORT[key] = val
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     try:
         os.makedirs(out, exist_ok=True)
-        with open(os.path.join(out, "parity_report.json"), "w") as f:
+        path = os.path.join(out, "parity_report.json")
+        if not REPORT and os.path.exists(path):
+            with open(path) as f:
+                REPORT.update(json.load(f))          # several pytest invocations append to one report
+        REPORT[key] = val
+        with open(path, "w") as f:
             json.dump(REPORT, f, indent=1, sort_keys=True)
     except OSError:
         pass
@@ -160,7 +164,8 @@ def test_plugin_surface_matches_engine(engines, yamnet_variables, mel, head):
     m2 = load_model("model_general_v3", framehop_prop=0.5, initialize=True)
     a3 = m2.predict(x).numpy()
     assert a3.shape[0] == O.frame_counts(len(x), 48)[2]
-    assert float(np.abs(a3[::2][:len(a)] - a).max()) <= 1e-3      # even half-hop frames are the whole-hop frames
+    k = min(len(a3[::2]), len(a))                                  # padding differs: whole-hop may add one frame
+    assert float(np.abs(a3[::2][:k] - a[:k]).max()) <= 1e-3       # even half-hop frames are the whole-hop frames
     with pytest.raises(ValueError):
         load_model("model_general_v3", framehop_prop=0.3, initialize=True)
 
@@ -207,4 +212,5 @@ def test_device_resident_entry_point(engines):
     assert np.array_equal(dact.cpu().numpy(), want)
     prof = e.profile_device_ptr(dx.data_ptr(), dx.numel(), 96)
     assert prof["pointwise"]["launches"] == 13 and prof["depthwise"]["launches"] == 13
-    assert all(v["ms"] > 0 for v in prof.values())
+    assert all(prof[k]["ms"] > 0 for k in ("frontend", "conv1", "depthwise", "pointwise", "pool_head"))
+    assert all(v["pw_launches"] == 1 and v["dw_launches"] == 1 for v in prof["layers"].values())
