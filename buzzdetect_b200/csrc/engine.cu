@@ -670,6 +670,7 @@ static int get_resampler(bd_engine* e, int src_rate, bd_engine::Resampler** out)
         r.up = up; r.down = down; r.taps_per_phase = tpp; r.d_taps = nullptr;
         BD_CHECK(e, cudaMalloc(&r.d_taps, taps.size() * sizeof(float)));
         BD_CHECK(e, cudaMemcpy(r.d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+        BD_CHECK(e, cudaDeviceSynchronize());   // the tap upload is not stream-ordered with s_compute
         it = e->resamplers.emplace(src_rate, r).first;
     }
     *out = &it->second;
@@ -713,7 +714,7 @@ int32_t bd_resample_host(bd_engine* e, const void* in, int32_t fmt, int32_t chan
     cudaError_t ce = cudaMalloc(&d_out, no * sizeof(float));
     if (ce != cudaSuccess) { cudaFree(d_in); BD_CHECK(e, ce); }
     int rc = 0;
-    ce = cudaMemcpy(d_in, in, in_bytes, cudaMemcpyHostToDevice);
+    ce = cudaMemcpyAsync(d_in, in, in_bytes, cudaMemcpyHostToDevice, e->s_compute);
     if (ce == cudaSuccess) {
         rc = bd_resample_device(e, d_in, fmt, channels, n_frames, src_rate, d_out, no, nullptr);
         if (rc == 0) ce = cudaMemcpy(out, d_out, no * sizeof(float), cudaMemcpyDeviceToHost);
@@ -733,7 +734,7 @@ int32_t bd_debug_logmel(bd_engine* e, const float* samples, int64_t n, int64_t n
     float *d_x = nullptr, *d_lm = nullptr;
     BD_CHECK(e, cudaMalloc(&d_x, std::max<int64_t>(n, 1) * sizeof(float)));
     BD_CHECK(e, cudaMalloc(&d_lm, n_frames * kMel * sizeof(float)));
-    BD_CHECK(e, cudaMemcpy(d_x, samples, n * sizeof(float), cudaMemcpyHostToDevice));
+    BD_CHECK(e, cudaMemcpyAsync(d_x, samples, n * sizeof(float), cudaMemcpyHostToDevice, e->s_compute));
     BD_CHECK(e, launch_logmel(d_x, n, 0, static_cast<int>(n_frames), e->d_tab, d_lm, e->num_sms, e->s_compute));
     e->launch_count++;
     BD_CHECK(e, cudaStreamSynchronize(e->s_compute));
@@ -752,13 +753,13 @@ int32_t bd_debug_pw_gemm(bd_engine* e, const float* A, const float* W, const flo
     __half *a_hi = nullptr, *a_lo = nullptr, *w_hi = nullptr, *w_lo = nullptr;
     BD_CHECK(e, cudaMalloc(&dB, N * sizeof(float)));
     BD_CHECK(e, cudaMalloc(&dC, nc * sizeof(float)));
-    BD_CHECK(e, cudaMemcpy(dB, bias, N * sizeof(float), cudaMemcpyHostToDevice));
+    BD_CHECK(e, cudaMemcpyAsync(dB, bias, N * sizeof(float), cudaMemcpyHostToDevice, e->s_compute));
     int rc = 0;
     if (precision == BD_PRECISION_FP32_SIMT) {
         BD_CHECK(e, cudaMalloc(&dA, na * sizeof(float)));
         BD_CHECK(e, cudaMalloc(&dW, nw * sizeof(float)));
-        BD_CHECK(e, cudaMemcpy(dA, A, na * sizeof(float), cudaMemcpyHostToDevice));
-        BD_CHECK(e, cudaMemcpy(dW, W, nw * sizeof(float), cudaMemcpyHostToDevice));
+        BD_CHECK(e, cudaMemcpyAsync(dA, A, na * sizeof(float), cudaMemcpyHostToDevice, e->s_compute));
+        BD_CHECK(e, cudaMemcpyAsync(dW, W, nw * sizeof(float), cudaMemcpyHostToDevice, e->s_compute));
         BD_CHECK(e, launch_pw_simt(dA, dW, dB, dC, M, N, K, e->s_compute));
     } else {
         BD_CHECK(e, pw_gemm_init_device());
@@ -766,14 +767,18 @@ int32_t bd_debug_pw_gemm(bd_engine* e, const float* A, const float* W, const flo
         split_f16(A, na, hi, lo);
         BD_CHECK(e, cudaMalloc(&a_hi, na * sizeof(__half)));
         BD_CHECK(e, cudaMalloc(&a_lo, na * sizeof(__half)));
-        BD_CHECK(e, cudaMemcpy(a_hi, hi.data(), na * sizeof(__half), cudaMemcpyHostToDevice));
-        BD_CHECK(e, cudaMemcpy(a_lo, lo.data(), na * sizeof(__half), cudaMemcpyHostToDevice));
+        BD_CHECK(e, cudaMemcpyAsync(a_hi, hi.data(), na * sizeof(__half), cudaMemcpyHostToDevice, e->s_compute));
+        BD_CHECK(e, cudaStreamSynchronize(e->s_compute));
+        BD_CHECK(e, cudaMemcpyAsync(a_lo, lo.data(), na * sizeof(__half), cudaMemcpyHostToDevice, e->s_compute));
+        BD_CHECK(e, cudaStreamSynchronize(e->s_compute));
         hi.resize(nw); lo.resize(nw);
         const float out_scale = split_weights_f16(W, nw, hi.data(), lo.data());
         BD_CHECK(e, cudaMalloc(&w_hi, nw * sizeof(__half)));
         BD_CHECK(e, cudaMalloc(&w_lo, nw * sizeof(__half)));
-        BD_CHECK(e, cudaMemcpy(w_hi, hi.data(), nw * sizeof(__half), cudaMemcpyHostToDevice));
-        BD_CHECK(e, cudaMemcpy(w_lo, lo.data(), nw * sizeof(__half), cudaMemcpyHostToDevice));
+        BD_CHECK(e, cudaMemcpyAsync(w_hi, hi.data(), nw * sizeof(__half), cudaMemcpyHostToDevice, e->s_compute));
+        BD_CHECK(e, cudaStreamSynchronize(e->s_compute));
+        BD_CHECK(e, cudaMemcpyAsync(w_lo, lo.data(), nw * sizeof(__half), cudaMemcpyHostToDevice, e->s_compute));
+        BD_CHECK(e, cudaStreamSynchronize(e->s_compute));
         PwGemmPlan plan;
         const char* perr = nullptr;
         cudaError_t pe = pw_gemm_make_plan(&plan, a_hi, a_lo, M, K, w_hi, w_lo, N, precision == BD_PRECISION_FP16X3 ? 3 : 1,
@@ -813,7 +818,7 @@ int32_t bd_debug_stage(bd_engine* e, const float* samples, int64_t n, int32_t ho
     float* d_act = nullptr;
     BD_CHECK(e, cudaMalloc(&d_x, std::max<int64_t>(n, 1) * sizeof(float)));
     BD_CHECK(e, cudaMalloc(&d_act, P * e->n_classes * sizeof(float)));
-    BD_CHECK(e, cudaMemcpy(d_x, samples, n * sizeof(float), cudaMemcpyHostToDevice));
+    BD_CHECK(e, cudaMemcpyAsync(d_x, samples, n * sizeof(float), cudaMemcpyHostToDevice, e->s_compute));
     int rc = enqueue_chunk(e, d_x, n, hop_frames, d_act, nullptr, P, e->s_compute, stage);
     if (rc == 0) {
         cudaError_t se = cudaStreamSynchronize(e->s_compute);

@@ -27,7 +27,9 @@ namespace {
 constexpr int kBM = 128;
 constexpr int kBK = 64;                      // 64 fp16 = 128 B = one swizzle row
 constexpr int kGemmThreads = 256;
-constexpr int kSmemBudget = 227 * 1024 - 2048;
+constexpr int kEpiStride = 36;                                   // floats per staged row (32 + 4 pad: conflict-free v4)
+constexpr int kEpiBytes = 4 * 32 * kEpiStride * 4;               // 4 epilogue warps x 32 rows
+constexpr int kSmemBudget = 227 * 1024 - 2048 - kEpiBytes;
 
 template <int BN, int NSPLIT>
 struct GemmCfg {
@@ -38,7 +40,7 @@ struct GemmCfg {
     static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
     static constexpr int kTmemCols = 2 * BN;                     // power of two for BN in {64,128,256}
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
     static_assert(kStages >= 2, "need at least a double buffer");
     static_assert(kTmemCols >= 32 && kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns");
 };
@@ -53,7 +55,8 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B operands need 1024-byte aligned tiles
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+    float* epi_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::kStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes + kEpiBytes);
     uint64_t* full_bar = bars;                    // [STAGES]
     uint64_t* empty_bar = bars + STAGES;          // [STAGES]
     uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
@@ -158,27 +161,37 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const int m_blk = t / n_tiles, n_blk = t % n_tiles;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            const int row = m_blk * kBM + q * 32 + lane;
+            const int row0 = m_blk * kBM + q * 32;                 // first row of this warp's TMEM lane quad
             const int n0 = n_blk * BN;
-            float* crow = C + static_cast<long long>(row) * N + n0;
+            float* stg = epi_stage + q * 32 * kEpiStride;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+            const int srow = lane >> 3, scol = (lane & 7) * 4;     // store mapping: 8 lanes cover one 128-byte row run
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), r);
                 tmem_ld_wait();
-                if (row < M) {
+                // thread = row: scale, bias, ReLU, stage the 32 columns of this row in shared memory
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
-                        float4 o;
-                        o.x = fmaxf(fmaf(__uint_as_float(r[j + 0]), out_scale, bv.x), 0.f);
-                        o.y = fmaxf(fmaf(__uint_as_float(r[j + 1]), out_scale, bv.y), 0.f);
-                        o.z = fmaxf(fmaf(__uint_as_float(r[j + 2]), out_scale, bv.z), 0.f);
-                        o.w = fmaxf(fmaf(__uint_as_float(r[j + 3]), out_scale, bv.w), 0.f);
-                        *reinterpret_cast<float4*>(crow + c0 + j) = o;
-                    }
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
+                    float4 o;
+                    o.x = fmaxf(fmaf(__uint_as_float(r[j + 0]), out_scale, bv.x), 0.f);
+                    o.y = fmaxf(fmaf(__uint_as_float(r[j + 1]), out_scale, bv.y), 0.f);
+                    o.z = fmaxf(fmaf(__uint_as_float(r[j + 2]), out_scale, bv.z), 0.f);
+                    o.w = fmaxf(fmaf(__uint_as_float(r[j + 3]), out_scale, bv.w), 0.f);
+                    *reinterpret_cast<float4*>(stg + lane * kEpiStride + j) = o;
                 }
+                __syncwarp();
+                // transposed read-back: each store instruction writes 4 rows x 128 contiguous bytes
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rl = i * 4 + srow;
+                    const float4 o = *reinterpret_cast<const float4*>(stg + rl * kEpiStride + scol);
+                    const int grow = row0 + rl;
+                    if (grow < M) *reinterpret_cast<float4*>(C + static_cast<long long>(grow) * N + n0 + c0 + scol) = o;
+                }
+                __syncwarp();
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
