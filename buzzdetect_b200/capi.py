@@ -39,7 +39,8 @@ class bd_weights(C.Structure):
 
 class bd_config(C.Structure):
     _fields_ = [("device", C.c_int32), ("precision", C.c_int32), ("early_patches", C.c_int32),
-                ("late_patches", C.c_int32), ("use_graph", C.c_int32), ("n_slots", C.c_int32)]
+                ("late_patches", C.c_int32), ("use_graph", C.c_int32), ("n_slots", C.c_int32),
+                ("fuse_mask", C.c_int32)]
 
 
 _f32p = C.POINTER(C.c_float)
@@ -130,7 +131,7 @@ class Engine:
 
     def __init__(self, device: int = 0, yamnet_variables: dict | None = None, embedder: str = "yamnet_k2",
                  head: tuple | None = None, precision: str | None = None, early_patches: int = 0,
-                 late_patches: int = 0, use_graph: bool = True, n_slots: int = 2):
+                 late_patches: int = 0, use_graph: bool = True, n_slots: int = 2, fuse_mask: int = -1):
         self._h = None
         lib = load_library()
         self._lib = lib
@@ -166,7 +167,8 @@ class Engine:
         w.head_kernel = hk.ctypes.data_as(_f32p)
         w.head_bias = hb.ctypes.data_as(_f32p)
         w.n_classes = self.n_classes
-        cfg = bd_config(self.device, PRECISION[precision], early_patches, late_patches, 1 if use_graph else 0, n_slots)
+        cfg = bd_config(self.device, PRECISION[precision], early_patches, late_patches, 1 if use_graph else 0, n_slots,
+                        fuse_mask)
         h = C.c_void_p()
         err = C.create_string_buffer(512)
         if lib.bd_engine_create(C.byref(cfg), C.byref(w), C.byref(h), err, 512):

@@ -71,6 +71,12 @@ cudaError_t pw_gemm_make_plan(PwGemmPlan* plan, const __half* a_hi, const __half
 float split_weights_f16(const float* w, size_t n, __half* hi, __half* lo);
 cudaError_t launch_pw_gemm(const PwGemmPlan& plan, const float* bias, float* C, int M, int num_sms,
                            cudaStream_t stream);
+// Fused separable block: depthwise 3x3 (+bias, ReLU) computed by producer warps straight into the GEMM's A tile.
+// X: [P,H,W,K] float32 NHWC; C: [P*(H/stride)*(W/stride), N].  Only the plan's weight maps (b_hi/b_lo) are used.
+// Requires (W/stride) % 4 == 0.
+cudaError_t launch_sep_fused(const PwGemmPlan& plan, const float* X, const float* dw_w, const float* dw_b,
+                             const float* bias, float* C, int P, int H, int W, int stride, int num_sms,
+                             cudaStream_t stream);
 
 // ---- resample.cu
 cudaError_t launch_resample(const void* in, int in_fmt /*0 f32, 1 s16*/, int channels, long long n_in_frames,

@@ -35,6 +35,7 @@ struct LayerDev {
     __half* w_lo = nullptr;
     PwGemmPlan plan;
     bool late = false;              // pointwise runs in the late phase
+    bool fused = false;             // depthwise computed inside the pointwise GEMM (sep_fused_kernel)
 };
 
 struct Slot {
@@ -74,6 +75,12 @@ struct bd_engine {
     float* d_F_late = nullptr;
     unsigned char* d_H_late = nullptr;
     size_t H_late_plane_bytes = 0;
+    float* d_F_early2 = nullptr;          // ping-pong partners for fused separable blocks (cannot run in place)
+    float* d_F_late2 = nullptr;
+    int first_late = 6;                   // index of the layer whose pointwise output starts the late phase (layer 7)
+    const void* dbg_ptr = nullptr;        // bd_debug_stage: where the requested stage's output lives
+    bool dbg_planes = false;
+    size_t dbg_plane_off = 0;
     std::vector<Slot> slots;
     std::map<GraphKey, cudaGraphExec_t> graphs;
     std::map<GraphKey, int64_t> graph_launches;
@@ -140,11 +147,52 @@ void mark(bd_engine* e, int cat, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------ the pipeline
 // Enqueue the whole chunk on `st`.  x: device audio, n samples.  Outputs are device pointers.
-// stop_stage >= 0 (debug): stop after that stage of the FIRST early sub-batch (see bd_debug_stage).
+// stop_stage >= 0 (debug): stop after that stage of the FIRST early sub-batch (see bd_debug_stage); the location of
+// the stage's output is left in e->dbg_*.
 int enqueue_chunk(bd_engine* e, const float* x, int64_t n, int hop_frames, float* d_act, float* d_emb,
                   int64_t P, cudaStream_t st, int stop_stage = -1) {
     const int prec = e->precision;
     const int dw_mode = prec == BD_PRECISION_FP32_SIMT ? 0 : (prec == BD_PRECISION_FP16X1 ? 1 : 2);
+    const int first_late = e->first_late;
+    auto stop_at = [&](int stage, const void* ptr, bool planes, size_t plane_off) {
+        if (stop_stage != stage) return false;
+        e->dbg_ptr = ptr; e->dbg_planes = planes; e->dbg_plane_off = plane_off;
+        return true;
+    };
+    // separable block L (index, >= 1) without fusion: depthwise in -> H planes, pointwise H -> out
+    auto unfused = [&](int L, const float* in, int np, unsigned char* H, size_t plane, int64_t row_off, float* out,
+                       bool do_dw, bool do_pw) -> int {
+        const LayerDev& l = e->layers[L];
+        float* o32 = reinterpret_cast<float*>(H) + row_off * l.d.cin;
+        __half* ohi = reinterpret_cast<__half*>(H) + row_off * l.d.cin;
+        __half* olo = reinterpret_cast<__half*>(H + plane) + row_off * l.d.cin;
+        if (do_dw) {
+            BD_CHECK(e, launch_depthwise(in, np, l.d.h_in, l.d.w_in, l.d.cin, l.d.stride, l.dw_w, l.dw_b, dw_mode, o32,
+                                         ohi, olo, st));
+            mark(e, CAT_DW + L - 1, st);
+            if (stop_at(2 * L, H + (dw_mode == 0 ? 4 : 2) * row_off * l.d.cin, dw_mode != 0, plane)) return 2;
+        }
+        if (do_pw) {
+            const int M = np * l.h_out * l.w_out;
+            if (prec == BD_PRECISION_FP32_SIMT) {
+                BD_CHECK(e, launch_pw_simt(reinterpret_cast<const float*>(H), l.w, l.b, out, M, l.d.cout, l.d.cin, st));
+            } else {
+                BD_CHECK(e, launch_pw_gemm(l.plan, l.b, out, M, e->num_sms, st));
+            }
+            mark(e, CAT_PW + L - 1, st);
+            if (stop_at(2 * L + 1, out, false, 0)) return 2;
+        }
+        return 0;
+    };
+    auto fused = [&](int L, const float* in, int np, float* out) -> int {
+        const LayerDev& l = e->layers[L];
+        BD_CHECK(e, launch_sep_fused(l.plan, in, l.dw_w, l.dw_b, l.b, out, np, l.d.h_in, l.d.w_in, l.d.stride, e->num_sms,
+                                     st));
+        mark(e, CAT_PW + L - 1, st);
+        if (stop_stage == 2 * L) { e->last_error = "stage is fused away (depthwise output stays in shared memory)"; return 1; }
+        if (stop_at(2 * L + 1, out, false, 0)) return 2;
+        return 0;
+    };
     for (int64_t big = 0; big < P; big += e->S2) {
         const int nb = static_cast<int>(std::min<int64_t>(e->S2, P - big));
         // ---------------- frontend: log-mel of the whole late batch in one launch (24.6 KB per patch)
@@ -152,66 +200,52 @@ int enqueue_chunk(bd_engine* e, const float* x, int64_t n, int hop_frames, float
             const int n_fr = (nb - 1) * hop_frames + kPatchFrames;
             BD_CHECK(e, launch_logmel(x, n, big * hop_frames, n_fr, e->d_tab, e->d_logmel, e->num_sms, st));
             mark(e, CAT_FRONTEND, st);
-            if (stop_stage == 0) return 0;
+            if (stop_at(0, e->d_logmel, false, 0)) return 0;
         }
+        const LayerDev& lb = e->layers[first_late];          // boundary layer: its pointwise output lives in F_late
         // ---------------- early phase
         for (int small = 0; small < nb; small += e->S1) {
             const int ns = std::min(e->S1, nb - small);
             const LayerDev& l1 = e->layers[0];
+            float* cur = e->d_F_early;
+            float* alt = e->d_F_early2;
             BD_CHECK(e, launch_conv1(e->d_logmel + static_cast<int64_t>(small) * hop_frames * kMel, hop_frames, ns, l1.w,
-                                     l1.b, e->d_F_early, st));
+                                     l1.b, cur, st));
             mark(e, CAT_CONV1, st);
-            if (stop_stage == 1) return 0;
-            for (int L = 1; L < BD_N_LAYERS; ++L) {
-                const LayerDev& l = e->layers[L];
-                const bool to_late = l.late;          // this depthwise feeds the late phase
-                unsigned char* H = to_late ? e->d_H_late : e->d_H_early;
-                const size_t plane = to_late ? e->H_late_plane_bytes : e->H_early_plane_bytes;
-                const int64_t row_off = to_late ? static_cast<int64_t>(small) * l.h_out * l.w_out : 0;
-                float* o32 = reinterpret_cast<float*>(H) + row_off * l.d.cin;
-                __half* ohi = reinterpret_cast<__half*>(H) + row_off * l.d.cin;
-                __half* olo = reinterpret_cast<__half*>(H + plane) + row_off * l.d.cin;
-                BD_CHECK(e, launch_depthwise(e->d_F_early, ns, l.d.h_in, l.d.w_in, l.d.cin, l.d.stride, l.dw_w, l.dw_b,
-                                             dw_mode, o32, ohi, olo, st));
-                mark(e, CAT_DW + L - 1, st);
-                if (stop_stage == 2 * L) return 0;
-                if (to_late) break;
-                const int M = ns * l.h_out * l.w_out;
-                if (prec == BD_PRECISION_FP32_SIMT) {
-                    BD_CHECK(e, launch_pw_simt(reinterpret_cast<const float*>(H), l.w, l.b, e->d_F_early, M, l.d.cout,
-                                               l.d.cin, st));
+            if (stop_at(1, cur, false, 0)) return 0;
+            for (int L = 1; L < first_late; ++L) {
+                int rc;
+                if (e->layers[L].fused) {
+                    rc = fused(L, cur, ns, alt);
+                    std::swap(cur, alt);
                 } else {
-                    BD_CHECK(e, launch_pw_gemm(l.plan, l.b, e->d_F_early, M, e->num_sms, st));
+                    rc = unfused(L, cur, ns, e->d_H_early, e->H_early_plane_bytes, 0, cur, true, true);
                 }
-                mark(e, CAT_PW + L - 1, st);
-                if (stop_stage == 2 * L + 1) return 0;
+                if (rc) return rc == 2 ? 0 : rc;
             }
+            const int64_t row_off = static_cast<int64_t>(small) * lb.h_out * lb.w_out;
+            int rc;
+            if (lb.fused) rc = fused(first_late, cur, ns, e->d_F_late + row_off * lb.d.cout);
+            else rc = unfused(first_late, cur, ns, e->d_H_late, e->H_late_plane_bytes, row_off, nullptr, true, false);
+            if (rc) return rc == 2 ? 0 : rc;
         }
         // ---------------- late phase
-        int first_late = 0;
-        for (int L = 1; L < BD_N_LAYERS; ++L) if (e->layers[L].late) { first_late = L; break; }
+        float* cur = e->d_F_late;
+        float* alt = e->d_F_late2;
         for (int L = first_late; L < BD_N_LAYERS; ++L) {
-            const LayerDev& l = e->layers[L];
-            if (L != first_late) {
-                BD_CHECK(e, launch_depthwise(e->d_F_late, nb, l.d.h_in, l.d.w_in, l.d.cin, l.d.stride, l.dw_w, l.dw_b,
-                                             dw_mode, reinterpret_cast<float*>(e->d_H_late),
-                                             reinterpret_cast<__half*>(e->d_H_late),
-                                             reinterpret_cast<__half*>(e->d_H_late + e->H_late_plane_bytes), st));
-                mark(e, CAT_DW + L - 1, st);
-                if (stop_stage == 2 * L) return 0;
-            }
-            const int M = nb * l.h_out * l.w_out;
-            if (prec == BD_PRECISION_FP32_SIMT) {
-                BD_CHECK(e, launch_pw_simt(reinterpret_cast<const float*>(e->d_H_late), l.w, l.b, e->d_F_late, M,
-                                           l.d.cout, l.d.cin, st));
+            int rc = 0;
+            if (L == first_late) {
+                if (!lb.fused) rc = unfused(L, nullptr, nb, e->d_H_late, e->H_late_plane_bytes, 0, cur, false, true);
+            } else if (e->layers[L].fused) {
+                rc = fused(L, cur, nb, alt);
+                std::swap(cur, alt);
             } else {
-                BD_CHECK(e, launch_pw_gemm(l.plan, l.b, e->d_F_late, M, e->num_sms, st));
+                rc = unfused(L, cur, nb, e->d_H_late, e->H_late_plane_bytes, 0, cur, true, true);
             }
-            mark(e, CAT_PW + L - 1, st);
-            if (stop_stage == 2 * L + 1) return 0;
+            if (rc) return rc == 2 ? 0 : rc;
         }
         const LayerDev& last = e->layers[BD_N_LAYERS - 1];
-        BD_CHECK(e, launch_pool_head(e->d_F_late, nb, last.h_out * last.w_out, e->d_headW, e->d_headB, e->n_classes,
+        BD_CHECK(e, launch_pool_head(cur, nb, last.h_out * last.w_out, e->d_headW, e->d_headB, e->n_classes,
                                      d_emb ? d_emb + big * kEmb : nullptr, d_act + big * e->n_classes, st));
         mark(e, CAT_POOL, st);
     }
@@ -328,7 +362,7 @@ void bd_engine_destroy(bd_engine* e) {
     for (auto& l : e->layers) { cudaFree(l.w_hi); cudaFree(l.w_lo); }
     for (auto& kv : e->resamplers) cudaFree(kv.second.d_taps);
     cudaFree(e->d_folded); cudaFree(e->d_tab); cudaFree(e->d_headW); cudaFree(e->d_headB);
-    cudaFree(e->d_logmel); cudaFree(e->d_F_early); cudaFree(e->d_H_early); cudaFree(e->d_F_late); cudaFree(e->d_H_late);
+    cudaFree(e->d_logmel); cudaFree(e->d_F_early2); cudaFree(e->d_F_late2); cudaFree(e->d_F_early); cudaFree(e->d_H_early); cudaFree(e->d_F_late); cudaFree(e->d_H_late);
     if (e->s_compute) cudaStreamDestroy(e->s_compute);
     if (e->s_in) cudaStreamDestroy(e->s_in);
     if (e->s_out) cudaStreamDestroy(e->s_out);
@@ -412,7 +446,9 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
     // ---- layers + buffer plan
     size_t f_early = 0, h_early = 0, f_late = 0, h_late = 0;    // elements per patch
     e->layers.resize(BD_N_LAYERS);
-    int first_late = 6;                                          // layer 7 (index 6): its depthwise output feeds the late phase
+    const int first_late = e->first_late;                        // layer 7 (index 6): its depthwise output feeds the late phase
+    // which separable blocks run fused: bit (L-2) for layer L; default = layers 2..6 (the activation-heavy ones)
+    const int fuse_mask = e->precision == BD_PRECISION_FP32_SIMT ? 0 : (cfg->fuse_mask < 0 ? 0x1F : cfg->fuse_mask);
     for (int L = 0; L < BD_N_LAYERS; ++L) {
         LayerDev& l = e->layers[L];
         l.d = w->layers[L];
@@ -420,6 +456,7 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
         l.h_out = l.d.h_in / l.d.stride;
         l.w_out = l.d.w_in / l.d.stride;
         l.late = L >= first_late;
+        l.fused = L >= 1 && ((fuse_mask >> (L - 1)) & 1) && (l.d.w_in / l.d.stride) % 4 == 0 && l.d.cin % 4 == 0;
         auto ptr = [&](int64_t o) -> const float* { return o >= 0 ? e->d_folded + o : nullptr; };
         l.dw_w = ptr(l.d.dw_w); l.dw_b = ptr(l.d.dw_b); l.w = ptr(l.d.w); l.b = ptr(l.d.b);
         const size_t out_px = static_cast<size_t>(l.h_out) * l.w_out;
@@ -441,7 +478,9 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
     e->H_early_plane_bytes = sizeof(__half) * h_early * e->S1;
     BD_CREATE(cudaMalloc(&e->d_H_early, sizeof(float) * h_early * e->S1));
     BD_CREATE(cudaMemset(e->d_H_early, 0, sizeof(float) * h_early * e->S1));
+    BD_CREATE(cudaMalloc(&e->d_F_early2, sizeof(float) * f_early * e->S1));
     BD_CREATE(cudaMalloc(&e->d_F_late, sizeof(float) * f_late * e->S2));
+    BD_CREATE(cudaMalloc(&e->d_F_late2, sizeof(float) * f_late * e->S2));
     e->H_late_plane_bytes = sizeof(__half) * h_late * e->S2;
     BD_CREATE(cudaMalloc(&e->d_H_late, sizeof(float) * h_late * e->S2));
     BD_CREATE(cudaMemset(e->d_H_late, 0, sizeof(float) * h_late * e->S2));
@@ -819,6 +858,7 @@ int32_t bd_debug_stage(bd_engine* e, const float* samples, int64_t n, int32_t ho
     BD_CHECK(e, cudaMalloc(&d_x, std::max<int64_t>(n, 1) * sizeof(float)));
     BD_CHECK(e, cudaMalloc(&d_act, P * e->n_classes * sizeof(float)));
     BD_CHECK(e, cudaMemcpyAsync(d_x, samples, n * sizeof(float), cudaMemcpyHostToDevice, e->s_compute));
+    e->dbg_ptr = nullptr;
     int rc = enqueue_chunk(e, d_x, n, hop_frames, d_act, nullptr, P, e->s_compute, stage);
     if (rc == 0) {
         cudaError_t se = cudaStreamSynchronize(e->s_compute);
@@ -826,34 +866,24 @@ int32_t bd_debug_stage(bd_engine* e, const float* samples, int64_t n, int32_t ho
     }
     if (rc == 0) {
         int64_t count = 0;
-        const void* src = nullptr;
-        bool planes = false;                // source is hi/lo fp16 planes
-        size_t plane_off = 0;
+        const void* src = e->dbg_ptr;
+        const bool planes = e->dbg_planes;
+        const size_t plane_off = e->dbg_plane_off;
         if (stage == 0) {
             count = (static_cast<int64_t>(P - 1) * hop_frames + kPatchFrames) * kMel;
-            src = e->d_logmel;
         } else if (stage == 1) {
             count = P * 48 * 32 * 32;
-            src = e->d_F_early;
         } else {
-            const int L = stage / 2;        // layer index (0-based): stage 2L = dw out, 2L+1 = pw out
-            const LayerDev& l = e->layers[L];
-            const bool is_dw = (stage % 2) == 0;
-            count = P * l.h_out * l.w_out * (is_dw ? l.d.cin : l.d.cout);
-            if (is_dw) {
-                src = l.late ? e->d_H_late : e->d_H_early;
-                plane_off = l.late ? e->H_late_plane_bytes : e->H_early_plane_bytes;
-                planes = e->precision != BD_PRECISION_FP32_SIMT;
-            } else {
-                src = l.late ? e->d_F_late : e->d_F_early;
-            }
+            const LayerDev& l = e->layers[stage / 2];   // stage 2L = depthwise out, 2L+1 = pointwise out of layer index L
+            count = P * l.h_out * l.w_out * ((stage % 2) == 0 ? l.d.cin : l.d.cout);
         }
-        if (count > out_capacity) {
+        if (src == nullptr) rc = fail(e, "debug stage was not reached");
+        if (rc == 0 && count > out_capacity) {
             rc = fail(e, "debug stage output buffer too small");
-        } else if (!planes) {
+        } else if (rc == 0 && !planes) {
             cudaError_t me = cudaMemcpy(out, src, count * sizeof(float), cudaMemcpyDeviceToHost);
             if (me != cudaSuccess) rc = fail(e, cudaGetErrorString(me));
-        } else {
+        } else if (rc == 0) {
             std::vector<__half> hi(count), lo(count);
             cudaMemcpy(hi.data(), src, count * sizeof(__half), cudaMemcpyDeviceToHost);
             if (e->precision == BD_PRECISION_FP16X3)

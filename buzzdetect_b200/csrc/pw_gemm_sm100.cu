@@ -207,6 +207,273 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
 }
 
+// ------------------------------------------------------------------------------------------ fused depthwise + pointwise
+// One separable block in one kernel:
+//     C[M,N] = relu( relu(DW3x3(X) + b_dw)[M,K] * W[N,K]^T * out_scale + b_pw )
+// The depthwise output never goes to HBM: eight producer warps compute it on the CUDA cores straight into the
+// SWIZZLE_128B K-major shared-memory tile that tcgen05.mma reads as its A operand (hi/lo fp16 planes), while warp 0
+// streams the weight tile with TMA.  Everything else (TMEM double buffering, epilogue) is the plain GEMM above.
+//
+// Producer mapping per 128-pixel x 64-channel k-block: thread = (channel quad, strip of 4 consecutive output pixels
+// along W); 256 threads x 2 strips.  The 3 x ((4-1)*STRIDE+3) input window and the 9 tap vectors sit in registers.
+// Element (row r, channel c) of the tile lives at  (r/8)*1024 + (r%8)*128 + (((c/8) ^ (r%8)) * 16) + (c%8)*2  bytes.
+constexpr int kFusedThreads = 512;
+constexpr int kProducerWarps = 8;
+
+template <int BN, int NSPLIT, int STRIDE>
+__global__ void __launch_bounds__(kFusedThreads, 1)
+sep_fused_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                 const float* __restrict__ X, const float* __restrict__ dw_w, const float* __restrict__ dw_b,
+                 const float* __restrict__ bias, float* __restrict__ C, int P, int H, int W, int K, int N,
+                 float out_scale) {
+    using Cfg = GemmCfg<BN, NSPLIT>;
+    constexpr int STAGES = Cfg::kStages;
+    constexpr int PB = STRIDE == 1 ? 1 : 0;
+    constexpr int R = 4;
+    constexpr int NC = (R - 1) * STRIDE + 3;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* epi_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::kStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes + kEpiBytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + STAGES;
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Ho = H / STRIDE, Wo = W / STRIDE;
+    const int M = P * Ho * Wo;
+    const int m_tiles = (M + kBM - 1) / kBM, n_tiles = N / BN;
+    const int num_tiles = m_tiles * n_tiles;
+    const int num_kb = (K + kBK - 1) / kBK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_b_hi);
+        if (NSPLIT > 1) tma_prefetch_desc(&map_b_lo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 1 + kProducerWarps);     // TMA expect_tx arrive + one arrive per producer warp
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================================================= TMA producer (weights only)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int n_blk = t % n_tiles;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char* sb = smem + stage * Cfg::kStageBytes + Cfg::kPlanes * Cfg::kATile;
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kPlanes * Cfg::kBTile);
+                    tma_load_2d(sb, &map_b_hi, &full_bar[stage], kb * kBK, n_blk * BN);
+                    if (NSPLIT > 1) tma_load_2d(sb + Cfg::kBTile, &map_b_lo, &full_bar[stage], kb * kBK, n_blk * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================= MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(kBM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
+                    const uint32_t a_lo = a_hi + Cfg::kATile;
+                    const uint32_t b_hi = a_hi + Cfg::kPlanes * Cfg::kATile;
+                    const uint32_t b_lo = b_hi + Cfg::kBTile;
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k) {
+                        const uint32_t koff = static_cast<uint32_t>(k) * 32u;
+                        const uint64_t da_hi = umma_desc_k128(a_hi + koff);
+                        const uint64_t db_hi = umma_desc_k128(b_hi + koff);
+                        umma_f16_ss(d_tmem, da_hi, db_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (NSPLIT > 1) {
+                            const uint64_t da_lo = umma_desc_k128(a_lo + koff);
+                            const uint64_t db_lo = umma_desc_k128(b_lo + koff);
+                            umma_f16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
+                            umma_f16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
+                        }
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 8) {
+        // ================================================================= depthwise producers (CUDA cores -> smem A)
+        const int pt = threadIdx.x - 256;
+        const int quad = pt & 15;                       // 4 channels of the 64-channel k-block
+        const int strip0 = pt >> 4;                     // strips strip0 and strip0 + 16 (4 output pixels each)
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int m_blk = t / n_tiles;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int c = kb * kBK + quad * 4;
+                const bool c_ok = c < K;
+                float4 kk[9];
+                float4 bdw = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c_ok) {
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) kk[i] = __ldg(reinterpret_cast<const float4*>(dw_w + i * K + c));
+                    bdw = __ldg(reinterpret_cast<const float4*>(dw_b + c));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) kk[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                unsigned char* a_hi = smem + stage * Cfg::kStageBytes;
+                unsigned char* a_lo = a_hi + Cfg::kATile;
+#pragma unroll 1
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    const int strip = strip0 + 16 * s2;
+                    const int m = m_blk * kBM + strip * R;
+                    float4 acc[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) acc[r] = bdw;
+                    const bool live = c_ok && m < M;            // M % 4 == 0: a strip is all valid or all padding
+                    if (live) {
+                        const int ow0 = m % Wo;
+                        const int tq = m / Wo;
+                        const int oh = tq % Ho;
+                        const long long p = tq / Ho;
+                        const float* inp = X + p * H * W * K + c;
+#pragma unroll
+                        for (int kh = 0; kh < 3; ++kh) {
+                            const int ih = oh * STRIDE + kh - PB;
+                            if (ih < 0 || ih >= H) continue;
+                            const float* rowp = inp + static_cast<long long>(ih) * W * K;
+                            float4 v[NC];
+#pragma unroll
+                            for (int j = 0; j < NC; ++j) {
+                                const int iw = ow0 * STRIDE - PB + j;
+                                v[j] = (iw >= 0 && iw < W)
+                                           ? __ldg(reinterpret_cast<const float4*>(rowp + static_cast<long long>(iw) * K))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+#pragma unroll
+                            for (int r = 0; r < R; ++r) {
+#pragma unroll
+                                for (int kw = 0; kw < 3; ++kw) {
+                                    const float4 x = v[r * STRIDE + kw];
+                                    const float4 w4 = kk[kh * 3 + kw];
+                                    acc[r].x = fmaf(x.x, w4.x, acc[r].x);
+                                    acc[r].y = fmaf(x.y, w4.y, acc[r].y);
+                                    acc[r].z = fmaf(x.z, w4.z, acc[r].z);
+                                    acc[r].w = fmaf(x.w, w4.w, acc[r].w);
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        float4 a = acc[r];
+                        if (live) {
+                            a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+                        } else {
+                            a = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        const int row = strip * R + r;
+                        const uint32_t off = static_cast<uint32_t>((row >> 3) * 1024 + (row & 7) * 128 +
+                                                                   ((((quad >> 1) ^ (row & 7))) << 4) + ((quad & 1) << 3));
+                        const __half h0 = __float2half_rn(a.x), h1 = __float2half_rn(a.y);
+                        const __half h2 = __float2half_rn(a.z), h3 = __float2half_rn(a.w);
+                        __half2 hp[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
+                        *reinterpret_cast<uint2*>(a_hi + off) = *reinterpret_cast<uint2*>(hp);
+                        if (NSPLIT > 1) {
+                            __half2 lp[2] = {__halves2half2(__float2half_rn(a.x - __half2float(h0)),
+                                                            __float2half_rn(a.y - __half2float(h1))),
+                                             __halves2half2(__float2half_rn(a.z - __half2float(h2)),
+                                                            __float2half_rn(a.w - __half2float(h3)))};
+                            *reinterpret_cast<uint2*>(a_lo + off) = *reinterpret_cast<uint2*>(lp);
+                        }
+                    }
+                }
+                fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the tensor-core proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================================================= epilogue (identical to pw_gemm_kernel)
+        const int q = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int m_blk = t / n_tiles, n_blk = t % n_tiles;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int row0 = m_blk * kBM + q * 32;
+            const int n0 = n_blk * BN;
+            float* stg = epi_stage + q * 32 * kEpiStride;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+            const int srow = lane >> 3, scol = (lane & 7) * 4;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
+                    float4 o;
+                    o.x = fmaxf(fmaf(__uint_as_float(r[j + 0]), out_scale, bv.x), 0.f);
+                    o.y = fmaxf(fmaf(__uint_as_float(r[j + 1]), out_scale, bv.y), 0.f);
+                    o.z = fmaxf(fmaf(__uint_as_float(r[j + 2]), out_scale, bv.z), 0.f);
+                    o.w = fmaxf(fmaf(__uint_as_float(r[j + 3]), out_scale, bv.w), 0.f);
+                    *reinterpret_cast<float4*>(stg + lane * kEpiStride + j) = o;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rl = i * 4 + srow;
+                    const float4 o = *reinterpret_cast<const float4*>(stg + rl * kEpiStride + scol);
+                    const int grow = row0 + rl;
+                    if (grow < M) *reinterpret_cast<float4*>(C + static_cast<long long>(grow) * N + n0 + c0 + scol) = o;
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -254,6 +521,23 @@ cudaError_t launch_t(const PwGemmPlan& p, const float* bias, float* C, int M, in
     return cudaGetLastError();
 }
 
+template <int BN, int NSPLIT, int STRIDE>
+cudaError_t set_attr_fused() {
+    return cudaFuncSetAttribute(sep_fused_kernel<BN, NSPLIT, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                GemmCfg<BN, NSPLIT>::kSmemBytes);
+}
+
+template <int BN, int NSPLIT, int STRIDE>
+cudaError_t launch_fused_t(const PwGemmPlan& p, const float* X, const float* dw_w, const float* dw_b, const float* bias,
+                           float* C, int P, int H, int W, int num_sms, cudaStream_t stream) {
+    const int M = P * (H / STRIDE) * (W / STRIDE);
+    const int tiles = ((M + kBM - 1) / kBM) * (p.N / BN);
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    sep_fused_kernel<BN, NSPLIT, STRIDE><<<grid, kFusedThreads, GemmCfg<BN, NSPLIT>::kSmemBytes, stream>>>(
+        p.b_hi, p.b_lo, X, dw_w, dw_b, bias, C, P, H, W, p.K, p.N, p.out_scale);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 float split_weights_f16(const float* w, size_t n, __half* hi, __half* lo) {
@@ -282,7 +566,35 @@ cudaError_t pw_gemm_init_device() {
     if ((e = set_attr<64, 3>()) != cudaSuccess) return e;
     if ((e = set_attr<128, 3>()) != cudaSuccess) return e;
     if ((e = set_attr<256, 3>()) != cudaSuccess) return e;
+#define BD_FUSED_ATTR(BN)                                                           \
+    if ((e = set_attr_fused<BN, 1, 1>()) != cudaSuccess) return e;                  \
+    if ((e = set_attr_fused<BN, 1, 2>()) != cudaSuccess) return e;                  \
+    if ((e = set_attr_fused<BN, 3, 1>()) != cudaSuccess) return e;                  \
+    if ((e = set_attr_fused<BN, 3, 2>()) != cudaSuccess) return e;
+    BD_FUSED_ATTR(64)
+    BD_FUSED_ATTR(128)
+    BD_FUSED_ATTR(256)
+#undef BD_FUSED_ATTR
     return cudaSuccess;
+}
+
+cudaError_t launch_sep_fused(const PwGemmPlan& p, const float* X, const float* dw_w, const float* dw_b,
+                             const float* bias, float* C, int P, int H, int W, int stride, int num_sms,
+                             cudaStream_t stream) {
+    if (P <= 0) return cudaSuccess;
+    if ((stride != 1 && stride != 2) || (W / stride) % 4 != 0 || p.K % 4 != 0) return cudaErrorInvalidValue;
+#define BD_FUSED(BN, NS)                                                                                         \
+    return stride == 1 ? launch_fused_t<BN, NS, 1>(p, X, dw_w, dw_b, bias, C, P, H, W, num_sms, stream)          \
+                       : launch_fused_t<BN, NS, 2>(p, X, dw_w, dw_b, bias, C, P, H, W, num_sms, stream)
+    if (p.nsplit == 1) {
+        if (p.block_n == 64) BD_FUSED(64, 1);
+        if (p.block_n == 128) BD_FUSED(128, 1);
+        BD_FUSED(256, 1);
+    }
+    if (p.block_n == 64) BD_FUSED(64, 3);
+    if (p.block_n == 128) BD_FUSED(128, 3);
+    BD_FUSED(256, 3);
+#undef BD_FUSED
 }
 
 cudaError_t pw_gemm_make_plan(PwGemmPlan* plan, const __half* a_hi, const __half* a_lo, int M_max, int K,

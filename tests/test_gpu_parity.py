@@ -86,14 +86,21 @@ def test_pw_gemm_matches_float64(engines, precision, M, N, K):
 
 
 # ------------------------------------------------------------------------------------------------ layer by layer
-@pytest.mark.parametrize("precision", ["fp32", "fp16x3", "fp16"])
-def test_every_stage_matches_oracle(engines, yamnet_variables, mel, precision):
-    e = engines(precision, early_patches=8, late_patches=16)
+@pytest.mark.parametrize("precision,fuse_mask", [("fp32", 0), ("fp16x3", 0), ("fp16", 0), ("fp16x3", 0x7FF),
+                                                 ("fp16", 0x7FF)])
+def test_every_stage_matches_oracle(engines, yamnet_variables, mel, precision, fuse_mask):
+    """fuse_mask 0: separate depthwise / pointwise kernels (every intermediate is observable);
+    0x7FF: layers 2..12 run as ONE fused kernel each (depthwise outputs stay in shared memory)."""
+    e = engines(precision, early_patches=8, late_patches=16, fuse_mask=fuse_mask)
     x = O.synth_audio(16000 * 5, seed=11)            # 6 patches
     taps = {}
     O.embed(x, yamnet_variables, mel, 96, taps=taps)
     worst = {}
     for stage in range(0, 28):
+        if stage >= 2 and stage % 2 == 0 and (fuse_mask >> (stage // 2 - 1)) & 1:
+            with pytest.raises(RuntimeError, match="fused away"):
+                e.debug_stage(x, stage)
+            continue
         if stage == 0:
             ref = taps["logmel"][:(6 - 1) * 96 + 96]
         elif stage == 1:
@@ -105,7 +112,7 @@ def test_every_stage_matches_oracle(engines, yamnet_variables, mel, precision):
         assert got.size == ref.size, (stage, got.size, ref.size)
         err = float(np.abs(got - ref.ravel()).max()) / max(float(np.abs(ref).max()), 1e-6)
         worst[stage] = err
-    _report(f"stages_{precision}", worst)
+    _report(f"stages_{precision}_fuse{fuse_mask:x}", worst)
     tol = 3e-2 if precision == "fp16" else 1e-4
     bad = {s: v for s, v in worst.items() if not v <= tol}
     assert not bad, bad
@@ -116,12 +123,12 @@ def _median_threshold(a):
     return float(np.median(a[:, 8]))
 
 
-@pytest.mark.parametrize("precision,hop,seconds", [
-    ("fp16x3", 96, 61.3), ("fp16x3", 48, 61.3), ("fp32", 96, 20.0), ("fp16x3", 96, 0.5), ("fp16x3", 96, 199.68),
-    ("fp16", 96, 61.3),
+@pytest.mark.parametrize("precision,hop,seconds,fuse_mask", [
+    ("fp16x3", 96, 61.3, -1), ("fp16x3", 48, 61.3, -1), ("fp32", 96, 20.0, -1), ("fp16x3", 96, 0.5, -1),
+    ("fp16x3", 96, 199.68, -1), ("fp16", 96, 61.3, -1), ("fp16x3", 96, 61.3, 0), ("fp16x3", 48, 33.1, 0x7FF),
 ])
-def test_predict_matches_oracle(engines, yamnet_variables, mel, head, precision, hop, seconds):
-    e = engines(precision, early_patches=16, late_patches=48)     # several early and late sub-batches
+def test_predict_matches_oracle(engines, yamnet_variables, mel, head, precision, hop, seconds, fuse_mask):
+    e = engines(precision, early_patches=16, late_patches=48, fuse_mask=fuse_mask)   # several early / late sub-batches
     n = int(round(seconds * 16000))
     x = O.synth_audio(n, seed=int(seconds * 10) + hop)
     act, emb = e.predict(x, hop, want_embeddings=True)
@@ -133,7 +140,7 @@ def test_predict_matches_oracle(engines, yamnet_variables, mel, head, precision,
     near = np.abs(want[:, 8] - thr) <= 1e-3
     flips = int(((act[:, 8] > thr) != (want[:, 8] > thr))[~near].sum())
     rounded_diff = int((np.round(act, 2) != np.round(want, 2)).sum())
-    _report(f"predict_{precision}_hop{hop}_{seconds}s", {"act_max_abs": a_err, "emb_max_rel": e_err, "flips": flips,
+    _report(f"predict_{precision}_hop{hop}_{seconds}s_fuse{fuse_mask}", {"act_max_abs": a_err, "emb_max_rel": e_err, "flips": flips,
                                                         "rounded_cells_differing": rounded_diff,
                                                         "cells": int(act.size), "act_range": [float(want.min()), float(want.max())]})
     if precision == "fp16":
@@ -211,6 +218,7 @@ def test_device_resident_entry_point(engines):
     assert P == want.shape[0]
     assert np.array_equal(dact.cpu().numpy(), want)
     prof = e.profile_device_ptr(dx.data_ptr(), dx.numel(), 96)
-    assert prof["pointwise"]["launches"] == 13 and prof["depthwise"]["launches"] == 13
+    assert prof["pointwise"]["launches"] == 13 and prof["depthwise"]["launches"] == 8   # layers 2..6 run fused
     assert all(prof[k]["ms"] > 0 for k in ("frontend", "conv1", "depthwise", "pointwise", "pool_head"))
-    assert all(v["pw_launches"] == 1 and v["dw_launches"] == 1 for v in prof["layers"].values())
+    assert all(v["pw_launches"] == 1 for v in prof["layers"].values())
+    assert [v["dw_launches"] for v in prof["layers"].values()] == [0] * 5 + [1] * 8
