@@ -447,8 +447,9 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
     size_t f_early = 0, h_early = 0, f_late = 0, h_late = 0;    // elements per patch
     e->layers.resize(BD_N_LAYERS);
     const int first_late = e->first_late;                        // layer 7 (index 6): its depthwise output feeds the late phase
-    // which separable blocks run fused: bit (L-2) for layer L; default = layers 2..6 (the activation-heavy ones)
-    const int fuse_mask = e->precision == BD_PRECISION_FP32_SIMT ? 0 : (cfg->fuse_mask < 0 ? 0x1F : cfg->fuse_mask);
+    // which separable blocks run fused: bit (L-2) for layer L.  Measured on B200 (profiles/fusion_r1.md): with the
+    // current register-fed producers only layer 3 (stride 2, K=64) beats the two-kernel path, so that is the default.
+    const int fuse_mask = e->precision == BD_PRECISION_FP32_SIMT ? 0 : (cfg->fuse_mask < 0 ? 0x2 : cfg->fuse_mask);
     for (int L = 0; L < BD_N_LAYERS; ++L) {
         LayerDev& l = e->layers[L];
         l.d = w->layers[L];

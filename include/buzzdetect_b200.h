@@ -67,7 +67,7 @@ typedef struct bd_config {
     int32_t use_graph;             /* 1 = capture and replay CUDA graphs per (n_samples, hop)               */
     int32_t n_slots;               /* in-flight host chunks for bd_submit_host (1..4, 0 = 2)                */
     int32_t fuse_mask;             /* bit (L-2): run separable layer L as ONE fused depthwise+pointwise kernel;
-                                      -1 = default (layers 2..6).  Ignored in BD_PRECISION_FP32_SIMT.         */
+                                      -1 = default (layer 3 only).  Ignored in BD_PRECISION_FP32_SIMT.         */
 } bd_config;
 
 int32_t bd_abi_version(void);
