@@ -38,6 +38,12 @@ cudaError_t launch_logmel(const float* x, long long n_valid, long long frame_beg
 // starts at row p*hop_frames of `logmel` (patches are views, never copied).  out: [P,48,32,32] float32 NHWC.
 cudaError_t launch_conv1(const float* logmel, int hop_frames, int P, const float* w9x32, const float* b32,
                          float* out, cudaStream_t stream);
+// layer 1 + the depthwise half of layer 2 in one kernel (the [48,32,32] layer-1 activation stays in shared memory).
+// Output = layer-2 depthwise activation [P*48*32, 32] in the same formats as launch_depthwise.
+cudaError_t layers_init_device();
+cudaError_t launch_conv1_dw2(const float* logmel, int hop_frames, int P, const float* w1, const float* b1,
+                             const float* dw_w, const float* dw_b, int out_mode, float* out_f32, __half* out_hi,
+                             __half* out_lo, cudaStream_t stream);
 // depthwise 3x3 (stride 1: pad 1/1, stride 2: pad 0/1), folded BN + ReLU.  in [P,H,W,C] float32 NHWC.
 // out_mode 0: float32 plane `out_f32` [P*Ho*Wo, C]
 // out_mode 1: fp16 hi plane only            (single-pass tensor-core GEMM operand)
@@ -71,6 +77,11 @@ cudaError_t pw_gemm_make_plan(PwGemmPlan* plan, const __half* a_hi, const __half
 float split_weights_f16(const float* w, size_t n, __half* hi, __half* lo);
 cudaError_t launch_pw_gemm(const PwGemmPlan& plan, const float* bias, float* C, int M, int num_sms,
                            cudaStream_t stream);
+// Layers 1 + 2 (conv1 -> depthwise -> pointwise 32->64) in one kernel; only the plan's weight maps are used.
+// C: [P*48*32, 64] float32.
+cudaError_t launch_l12_fused(const PwGemmPlan& plan, const float* logmel, int hop_frames, int P, const float* w1,
+                             const float* b1, const float* dw_w, const float* dw_b, const float* bias, float* C,
+                             int num_sms, cudaStream_t stream);
 // Fused separable block: depthwise 3x3 (+bias, ReLU) computed by producer warps straight into the GEMM's A tile.
 // X: [P,H,W,K] float32 NHWC; C: [P*(H/stride)*(W/stride), N].  Only the plan's weight maps (b_hi/b_lo) are used.
 // Requires (W/stride) % 4 == 0.

@@ -10,6 +10,7 @@
 // written back; HBM traffic is essentially the audio in and the activations out.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -78,6 +79,8 @@ struct bd_engine {
     float* d_F_early2 = nullptr;          // ping-pong partners for fused separable blocks (cannot run in place)
     float* d_F_late2 = nullptr;
     int first_late = 6;                   // index of the layer whose pointwise output starts the late phase (layer 7)
+    bool fuse_conv1 = true;               // layer 1 + layer-2 depthwise in one kernel (conv1_dw2_kernel)
+    bool fuse_l12 = true;                 // layers 1 + 2 entirely in one kernel (l12_fused_kernel, tensor-core modes)
     const void* dbg_ptr = nullptr;        // bd_debug_stage: where the requested stage's output lives
     bool dbg_planes = false;
     size_t dbg_plane_off = 0;
@@ -209,11 +212,38 @@ int enqueue_chunk(bd_engine* e, const float* x, int64_t n, int hop_frames, float
             const LayerDev& l1 = e->layers[0];
             float* cur = e->d_F_early;
             float* alt = e->d_F_early2;
-            BD_CHECK(e, launch_conv1(e->d_logmel + static_cast<int64_t>(small) * hop_frames * kMel, hop_frames, ns, l1.w,
-                                     l1.b, cur, st));
-            mark(e, CAT_CONV1, st);
-            if (stop_at(1, cur, false, 0)) return 0;
-            for (int L = 1; L < first_late; ++L) {
+            const float* lm0 = e->d_logmel + static_cast<int64_t>(small) * hop_frames * kMel;
+            int L0 = 1;
+            if (e->fuse_l12) {
+                // layers 1 + 2 (conv1 -> depthwise -> pointwise) in one kernel: log-mel in, layer-2 output out
+                const LayerDev& l2 = e->layers[1];
+                BD_CHECK(e, launch_l12_fused(l2.plan, lm0, hop_frames, ns, l1.w, l1.b, l2.dw_w, l2.dw_b, l2.b, cur,
+                                             e->num_sms, st));
+                mark(e, CAT_CONV1, st);
+                if (stop_stage == 1 || stop_stage == 2) {
+                    e->last_error = "stage is fused away (layers 1-2 run as one kernel)";
+                    return 1;
+                }
+                if (stop_at(3, cur, false, 0)) return 0;
+                L0 = 2;
+            } else if (e->fuse_conv1 && !e->layers[1].fused) {
+                // layer 1 + layer-2 depthwise in one kernel, then layer-2 pointwise
+                const LayerDev& l2 = e->layers[1];
+                BD_CHECK(e, launch_conv1_dw2(lm0, hop_frames, ns, l1.w, l1.b, l2.dw_w, l2.dw_b, dw_mode,
+                                             reinterpret_cast<float*>(e->d_H_early), reinterpret_cast<__half*>(e->d_H_early),
+                                             reinterpret_cast<__half*>(e->d_H_early + e->H_early_plane_bytes), st));
+                mark(e, CAT_CONV1, st);
+                if (stop_stage == 1) { e->last_error = "stage is fused away (layer-1 output stays in shared memory)"; return 1; }
+                if (stop_at(2, e->d_H_early, dw_mode != 0, e->H_early_plane_bytes)) return 0;
+                const int rc2 = unfused(1, nullptr, ns, e->d_H_early, e->H_early_plane_bytes, 0, cur, false, true);
+                if (rc2) return rc2 == 2 ? 0 : rc2;
+                L0 = 2;
+            } else {
+                BD_CHECK(e, launch_conv1(lm0, hop_frames, ns, l1.w, l1.b, cur, st));
+                mark(e, CAT_CONV1, st);
+                if (stop_at(1, cur, false, 0)) return 0;
+            }
+            for (int L = L0; L < first_late; ++L) {
                 int rc;
                 if (e->layers[L].fused) {
                     rc = fused(L, cur, ns, alt);
@@ -412,6 +442,7 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
     BD_CREATE(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
     BD_CREATE(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
     BD_CREATE(frontend_init_device());
+    BD_CREATE(layers_init_device());
     if (e->precision != BD_PRECISION_FP32_SIMT) BD_CREATE(pw_gemm_init_device());
 
     // ---- weights
@@ -449,7 +480,11 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
     const int first_late = e->first_late;                        // layer 7 (index 6): its depthwise output feeds the late phase
     // which separable blocks run fused: bit (L-2) for layer L.  Measured on B200 (profiles/fusion_r1.md): with the
     // current register-fed producers only layer 3 (stride 2, K=64) beats the two-kernel path, so that is the default.
-    const int fuse_mask = e->precision == BD_PRECISION_FP32_SIMT ? 0 : (cfg->fuse_mask < 0 ? 0x2 : cfg->fuse_mask);
+    const int fuse_mask = e->precision == BD_PRECISION_FP32_SIMT ? 0 : (cfg->fuse_mask < 0 ? 0x2 : (cfg->fuse_mask & 0x1FFF));
+    e->fuse_conv1 = cfg->fuse_mask < 0 || (cfg->fuse_mask & BD_FUSE_CONV1_DW2) != 0;
+    // measured (profiles/fusion_r1.md): the single-kernel layers-1+2 path is latency bound (1.18 ms per audio-hour vs
+    // 0.44 + 0.70 for conv1_dw2 + pointwise), so it is opt-in
+    e->fuse_l12 = e->precision != BD_PRECISION_FP32_SIMT && cfg->fuse_mask >= 0 && (cfg->fuse_mask & BD_FUSE_L12) != 0;
     for (int L = 0; L < BD_N_LAYERS; ++L) {
         LayerDev& l = e->layers[L];
         l.d = w->layers[L];
@@ -475,16 +510,20 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
     }
     if (e->layers.back().d.cout != kEmb) return bail("last layer must have 1024 channels");
     BD_CREATE(cudaMalloc(&e->d_logmel, sizeof(float) * kMel * (static_cast<size_t>(e->S2) * kPatchFrames)));
+    // experiment knob: extra bytes between the hi and lo planes (decorrelates the DRAM mapping of the two lock-step
+    // read streams of the pointwise GEMMs)
+    size_t plane_pad = 0;
+    if (const char* pp = getenv("BD_PLANE_PAD")) plane_pad = static_cast<size_t>(atoll(pp)) & ~size_t(1023);
     BD_CREATE(cudaMalloc(&e->d_F_early, sizeof(float) * f_early * e->S1));
-    e->H_early_plane_bytes = sizeof(__half) * h_early * e->S1;
-    BD_CREATE(cudaMalloc(&e->d_H_early, sizeof(float) * h_early * e->S1));
-    BD_CREATE(cudaMemset(e->d_H_early, 0, sizeof(float) * h_early * e->S1));
+    e->H_early_plane_bytes = sizeof(__half) * h_early * e->S1 + plane_pad;
+    BD_CREATE(cudaMalloc(&e->d_H_early, sizeof(float) * h_early * e->S1 + plane_pad));
+    BD_CREATE(cudaMemset(e->d_H_early, 0, sizeof(float) * h_early * e->S1 + plane_pad));
     BD_CREATE(cudaMalloc(&e->d_F_early2, sizeof(float) * f_early * e->S1));
     BD_CREATE(cudaMalloc(&e->d_F_late, sizeof(float) * f_late * e->S2));
     BD_CREATE(cudaMalloc(&e->d_F_late2, sizeof(float) * f_late * e->S2));
-    e->H_late_plane_bytes = sizeof(__half) * h_late * e->S2;
-    BD_CREATE(cudaMalloc(&e->d_H_late, sizeof(float) * h_late * e->S2));
-    BD_CREATE(cudaMemset(e->d_H_late, 0, sizeof(float) * h_late * e->S2));
+    e->H_late_plane_bytes = sizeof(__half) * h_late * e->S2 + plane_pad;
+    BD_CREATE(cudaMalloc(&e->d_H_late, sizeof(float) * h_late * e->S2 + plane_pad));
+    BD_CREATE(cudaMemset(e->d_H_late, 0, sizeof(float) * h_late * e->S2 + plane_pad));
 
     // ---- tensor-core operands: weight planes + TMA descriptors
     if (e->precision != BD_PRECISION_FP32_SIMT) {

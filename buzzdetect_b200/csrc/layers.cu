@@ -22,14 +22,13 @@ __global__ void __launch_bounds__(256) conv1_kernel(const float* __restrict__ lo
     for (int i = threadIdx.x; i < 9 * 32; i += blockDim.x) sw[i] = w[i];
     if (threadIdx.x < 32) sb[threadIdx.x] = b[threadIdx.x];
     __syncthreads();
-    const long long total = static_cast<long long>(P) * 48 * 32 * 8;
-    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int cg = static_cast<int>(idx & 7);
-        const long long pix = idx >> 3;
-        const int ow = static_cast<int>(pix & 31);
-        const int oh = static_cast<int>((pix >> 5) % 48);
-        const long long p = pix / (48 * 32);
+    // one block = one output row (32 pixels x 8 channel groups) of one patch: no per-thread division
+    const int cg = threadIdx.x & 7;
+    const int ow = threadIdx.x >> 3;
+    for (unsigned bid = blockIdx.x; bid < static_cast<unsigned>(P) * 48u; bid += gridDim.x) {
+        const long long p = bid / 48u;
+        const int oh = static_cast<int>(bid - static_cast<unsigned>(p) * 48u);
+        const long long pix = (p * 48 + oh) * 32 + ow;
         const float* in = logmel + p * hop_frames * kMel;
         float4 acc = make_float4(sb[cg * 4 + 0], sb[cg * 4 + 1], sb[cg * 4 + 2], sb[cg * 4 + 3]);
 #pragma unroll
@@ -53,6 +52,136 @@ __global__ void __launch_bounds__(256) conv1_kernel(const float* __restrict__ lo
     }
 }
 
+// ------------------------------------------------------------------------------------------ conv1 + depthwise(layer 2)
+// Layer 1 (3x3/2 conv, 1 -> 32) and the depthwise half of layer 2 in one kernel: the [48,32,32] layer-1 activation
+// (196 KB per patch, the largest tensor of the net after layer-2's output) is never written to or read from HBM.
+// One CTA = 8 output rows x 32 columns x 32 channels of one patch:
+//   1. stage the 21 x 64 log-mel rows the tile needs in shared memory (zero beyond row 95 / column 63: conv1's SAME pad)
+//   2. compute the 10 x 34 x 32 layer-1 tile (1-pixel halo; ZERO outside the 48 x 32 image: the depthwise SAME pad)
+//   3. depthwise 3x3 stride 1 from shared memory, +bias, ReLU, emit fp32 / fp16 hi / hi+lo planes
+constexpr int kC1Rows = 8;                                   // output rows per CTA (48 = 6 tiles)
+constexpr int kC1TileH = kC1Rows + 2, kC1TileW = 34;
+constexpr int kC1LmRows = 2 * kC1TileH + 1, kC1LmStride = 66;
+constexpr int kC1LmFloats = (kC1LmRows * kC1LmStride + 3) & ~3;          // keeps the float4 weight table 16-byte aligned
+constexpr int kC1SmemBytes = (kC1TileH * kC1TileW * 32 + kC1LmFloats + 9 * 32 + 32) * 4;
+
+template <int OUT_MODE>
+__global__ void __launch_bounds__(256) conv1_dw2_kernel(const float* __restrict__ logmel, int hop_frames, int P,
+                                                        const float* __restrict__ w1, const float* __restrict__ b1,
+                                                        const float* __restrict__ dw_w, const float* __restrict__ dw_b,
+                                                        float* __restrict__ out_f32, __half* __restrict__ out_hi,
+                                                        __half* __restrict__ out_lo) {
+    extern __shared__ __align__(16) float c1_smem[];
+    float* c1 = c1_smem;                                     // [10][34][32]
+    float* lm = c1 + kC1TileH * kC1TileW * 32;               // [21][66]
+    float* sw = lm + kC1LmFloats;                            // [9][32]
+    float* sb = sw + 9 * 32;                                 // [32]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 9 * 32; i += 256) sw[i] = w1[i];
+    if (tid < 32) sb[tid] = b1[tid];
+    const int cg = tid & 7;                                  // channel quad (both phases)
+    const float4 bdw = __ldg(reinterpret_cast<const float4*>(dw_b + cg * 4));
+
+    const unsigned tiles_per_patch = 48 / kC1Rows;
+    for (unsigned bid = blockIdx.x; bid < static_cast<unsigned>(P) * tiles_per_patch; bid += gridDim.x) {
+        const long long p = bid / tiles_per_patch;
+        const int r0 = static_cast<int>(bid - static_cast<unsigned>(p) * tiles_per_patch) * kC1Rows;
+        const float* in = logmel + p * hop_frames * kMel;
+        __syncthreads();                                     // previous tile fully consumed (and sw/sb visible)
+        // ---- 1. log-mel rows 2*(r0-1) .. 2*(r0-1)+20, columns 0..64 (column 64 and rows >= 96 are padding)
+        const int lm_row0 = 2 * (r0 - 1);
+        for (int i = tid; i < kC1LmRows * 65; i += 256) {
+            const int rr = i / 65, cc = i - rr * 65;
+            const int gr = lm_row0 + rr;
+            lm[rr * kC1LmStride + cc] = (gr >= 0 && gr < kPatchFrames && cc < kMel) ? __ldg(in + gr * kMel + cc) : 0.f;
+        }
+        __syncthreads();
+        // ---- 2. layer-1 tile with halo: local (tr, tc) <-> image (r0 - 1 + tr, tc - 1); tap weights in registers
+        float4 w1r[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) w1r[i] = *reinterpret_cast<const float4*>(sw + i * 32 + cg * 4);
+        const float4 b1r = *reinterpret_cast<const float4*>(sb + cg * 4);
+        for (int i = tid; i < kC1TileH * kC1TileW * 8; i += 256) {
+            const int px = i >> 3;                           // cg == i & 7 == tid & 7 (256 % 8 == 0)
+            const int tr = px / kC1TileW, tc = px - tr * kC1TileW;
+            const int ir = r0 - 1 + tr, ic = tc - 1;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ir >= 0 && ir < 48 && ic >= 0 && ic < 32) {
+                a = b1r;
+                const float* l0 = lm + (2 * tr) * kC1LmStride + 2 * ic;      // log-mel row 2*ir - lm_row0 = 2*tr
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const float v = l0[kh * kC1LmStride + kw];
+                        const float4 wk = w1r[kh * 3 + kw];
+                        a.x = fmaf(v, wk.x, a.x);
+                        a.y = fmaf(v, wk.y, a.y);
+                        a.z = fmaf(v, wk.z, a.z);
+                        a.w = fmaf(v, wk.w, a.w);
+                    }
+                }
+                a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+            }
+            *reinterpret_cast<float4*>(c1 + px * 32 + cg * 4) = a;
+        }
+        __syncthreads();
+        // ---- 3. depthwise 3x3 stride 1: thread = (row, strip of 4 columns, channel quad); 512 items, 2 per thread
+        float4 kk[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) kk[i] = __ldg(reinterpret_cast<const float4*>(dw_w + i * 32 + cg * 4));
+#pragma unroll 1
+        for (int it = 0; it < 2; ++it) {
+            const int item = tid + 256 * it;
+            const int ws = (item >> 3) & 7, orow = item >> 6;          // strip 0..7, local output row 0..7
+            float4 acc[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] = bdw;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+                const float* rowp = c1 + ((orow + kh) * kC1TileW + ws * 4) * 32 + cg * 4;   // tile col = image col + 1 - 1 + kw
+                float4 v[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) v[j] = *reinterpret_cast<const float4*>(rowp + j * 32);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const float4 x = v[r + kw];
+                        const float4 w4 = kk[kh * 3 + kw];
+                        acc[r].x = fmaf(x.x, w4.x, acc[r].x);
+                        acc[r].y = fmaf(x.y, w4.y, acc[r].y);
+                        acc[r].z = fmaf(x.z, w4.z, acc[r].z);
+                        acc[r].w = fmaf(x.w, w4.w, acc[r].w);
+                    }
+                }
+            }
+            const long long pix0 = (p * 48 + r0 + orow) * 32 + ws * 4;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                float4 a = acc[r];
+                a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+                const long long o = (pix0 + r) * 32 + cg * 4;
+                if (OUT_MODE == 0) {
+                    *reinterpret_cast<float4*>(out_f32 + o) = a;
+                } else {
+                    const __half h0 = __float2half_rn(a.x), h1 = __float2half_rn(a.y);
+                    const __half h2 = __float2half_rn(a.z), h3 = __float2half_rn(a.w);
+                    __half2 hp[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
+                    *reinterpret_cast<uint2*>(out_hi + o) = *reinterpret_cast<uint2*>(hp);
+                    if (OUT_MODE == 2) {
+                        __half2 lp[2] = {__halves2half2(__float2half_rn(a.x - __half2float(h0)),
+                                                        __float2half_rn(a.y - __half2float(h1))),
+                                         __halves2half2(__float2half_rn(a.z - __half2float(h2)),
+                                                        __float2half_rn(a.w - __half2float(h3)))};
+                        *reinterpret_cast<uint2*>(out_lo + o) = *reinterpret_cast<uint2*>(lp);
+                    }
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ depthwise
 // thread = (strip of R consecutive output pixels along W, 4 channels).  The 3 x ((R-1)*STRIDE+3) input window and
 // the 9 weight vectors live in registers, so each input float4 is loaded once per strip instead of once per tap
@@ -64,18 +193,23 @@ __global__ void __launch_bounds__(256) depthwise_kernel(const float* __restrict_
                                                         const float* __restrict__ w, const float* __restrict__ b,
                                                         float* __restrict__ out_f32, __half* __restrict__ out_hi,
                                                         __half* __restrict__ out_lo) {
-    const int Ho = H / STRIDE, Wo = W / STRIDE, C4 = C >> 2, WS = Wo / R;
+    // C/4 and Wo/R are powers of two for every YAMNet layer, so (channel quad, strip, row) come from shifts and masks;
+    // the only division is one 32-bit block-uniform one.  (64-bit div/mod per thread cost more than the 36 FMAs.)
+    const int Ho = H / STRIDE, Wo = W / STRIDE;
     constexpr int PB = STRIDE == 1 ? 1 : 0;
     constexpr int NC = (R - 1) * STRIDE + 3;
-    const long long total = static_cast<long long>(P) * Ho * WS * C4;
-    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int c4 = static_cast<int>(idx % C4);
-        long long t = idx / C4;
-        const int ws = static_cast<int>(t % WS);
-        t /= WS;
-        const int oh = static_cast<int>(t % Ho);
-        const long long p = t / Ho;
+    const unsigned c4_bits = 31u - __clz(static_cast<unsigned>(C >> 2));
+    const unsigned ws_bits = 31u - __clz(static_cast<unsigned>(Wo / R));
+    const unsigned items = static_cast<unsigned>(Ho) << (ws_bits + c4_bits);       // per patch
+    const unsigned bpp = (items + blockDim.x - 1) / blockDim.x;                     // blocks per patch
+    for (unsigned bid = blockIdx.x; bid < static_cast<unsigned>(P) * bpp; bid += gridDim.x) {
+        const unsigned pi = bid / bpp;
+        const unsigned item = (bid - pi * bpp) * blockDim.x + threadIdx.x;
+        if (item >= items) continue;
+        const int c4 = static_cast<int>(item & ((1u << c4_bits) - 1u));
+        const int ws = static_cast<int>((item >> c4_bits) & ((1u << ws_bits) - 1u));
+        const int oh = static_cast<int>(item >> (c4_bits + ws_bits));
+        const long long p = pi;
         const int ow0 = ws * R;
         const float* inp = in + p * H * W * C + c4 * 4;
         float4 k[9];
@@ -226,8 +360,34 @@ inline int grid_for(long long total, int block, int cap) {
 cudaError_t launch_conv1(const float* logmel, int hop_frames, int P, const float* w, const float* b, float* out,
                          cudaStream_t stream) {
     if (P <= 0) return cudaSuccess;
-    const long long total = static_cast<long long>(P) * 48 * 32 * 8;
-    conv1_kernel<<<grid_for(total, 256, 148 * 64), 256, 0, stream>>>(logmel, hop_frames, P, w, b, out);
+    const long long blocks = static_cast<long long>(P) * 48;
+    if (blocks >= (1LL << 31)) return cudaErrorInvalidValue;
+    conv1_kernel<<<static_cast<int>(blocks < 148LL * 64 ? blocks : 148LL * 64), 256, 0, stream>>>(logmel, hop_frames, P,
+                                                                                                  w, b, out);
+    return cudaGetLastError();
+}
+
+cudaError_t layers_init_device() {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(conv1_dw2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1SmemBytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv1_dw2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1SmemBytes)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(conv1_dw2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1SmemBytes);
+}
+
+cudaError_t launch_conv1_dw2(const float* logmel, int hop_frames, int P, const float* w1, const float* b1,
+                             const float* dw_w, const float* dw_b, int out_mode, float* out_f32, __half* out_hi,
+                             __half* out_lo, cudaStream_t stream) {
+    if (P <= 0) return cudaSuccess;
+    if (out_mode < 0 || out_mode > 2) return cudaErrorInvalidValue;
+    const long long blocks = static_cast<long long>(P) * (48 / kC1Rows);
+    if (blocks >= (1LL << 31)) return cudaErrorInvalidValue;
+    const int grid = static_cast<int>(blocks < 148LL * 32 ? blocks : 148LL * 32);
+    if (out_mode == 0)
+        conv1_dw2_kernel<0><<<grid, 256, kC1SmemBytes, stream>>>(logmel, hop_frames, P, w1, b1, dw_w, dw_b, out_f32, out_hi, out_lo);
+    else if (out_mode == 1)
+        conv1_dw2_kernel<1><<<grid, 256, kC1SmemBytes, stream>>>(logmel, hop_frames, P, w1, b1, dw_w, dw_b, out_f32, out_hi, out_lo);
+    else
+        conv1_dw2_kernel<2><<<grid, 256, kC1SmemBytes, stream>>>(logmel, hop_frames, P, w1, b1, dw_w, dw_b, out_f32, out_hi, out_lo);
     return cudaGetLastError();
 }
 
@@ -238,8 +398,12 @@ cudaError_t launch_depthwise(const float* in, int P, int H, int W, int C, int st
     if (out_mode < 0 || out_mode > 2) return cudaErrorInvalidValue;
     const int Wo = W / stride;
     const int R = (Wo % 4 == 0) ? 4 : ((Wo % 2 == 0) ? 2 : 1);
-    const long long total = static_cast<long long>(P) * (H / stride) * (Wo / R) * (C / 4);
-    const int grid = grid_for(total, 256, 148 * 64);
+    const unsigned c4 = static_cast<unsigned>(C / 4), wsn = static_cast<unsigned>(Wo / R);
+    if ((c4 & (c4 - 1)) || (wsn & (wsn - 1))) return cudaErrorInvalidValue;      // shift/mask indexing (see kernel)
+    const long long items = static_cast<long long>(H / stride) * wsn * c4;
+    const long long blocks = static_cast<long long>(P) * ((items + 255) / 256);
+    if (blocks >= (1LL << 31)) return cudaErrorInvalidValue;
+    const int grid = static_cast<int>(blocks < 148LL * 64 ? blocks : 148LL * 64);
 #define BD_DW(S, RR, MODE) \
     depthwise_kernel<S, RR, MODE><<<grid, 256, 0, stream>>>(in, P, H, W, C, w, b, out_f32, out_hi, out_lo)
 #define BD_DW_MODE(S, RR)                          \

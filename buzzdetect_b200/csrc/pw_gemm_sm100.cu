@@ -329,6 +329,8 @@ sep_fused_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_cons
         // ================================================================= depthwise producers (CUDA cores -> smem A)
         const int pt = threadIdx.x - 256;
         const int quad = pt & 15;                       // 4 channels of the 64-channel k-block
+        const int wo_bits = 31 - __clz(Wo);
+        const float inv_ho = 1.0f / static_cast<float>(Ho);
         const int strip0 = pt >> 4;                     // strips strip0 and strip0 + 16 (4 output pixels each)
         int stage = 0;
         uint32_t phase = 0;
@@ -359,10 +361,12 @@ sep_fused_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_cons
                     for (int r = 0; r < R; ++r) acc[r] = bdw;
                     const bool live = c_ok && m < M;            // M % 4 == 0: a strip is all valid or all padding
                     if (live) {
-                        const int ow0 = m % Wo;
-                        const int tq = m / Wo;
-                        const int oh = tq % Ho;
-                        const long long p = tq / Ho;
+                        // Wo is a power of two; tq < 2^23 so the float reciprocal division by Ho is exact
+                        const int ow0 = m & (Wo - 1);
+                        const int tq = m >> wo_bits;
+                        const int pq = static_cast<int>((static_cast<float>(tq) + 0.5f) * inv_ho);
+                        const int oh = tq - pq * Ho;
+                        const long long p = pq;
                         const float* inp = X + p * H * W * K + c;
 #pragma unroll
                         for (int kh = 0; kh < 3; ++kh) {
@@ -474,6 +478,222 @@ sep_fused_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_cons
     }
 }
 
+// ------------------------------------------------------------------------------------------ layers 1 + 2 in one kernel
+// conv 3x3/2 (1->32) -> depthwise 3x3 (32) -> pointwise 32->64, all with folded BN + ReLU, per 128-pixel tile
+// (4 image rows x 32 columns of one patch).  Reads 3.4 KB of log-mel, writes 32 KB of layer-2 output; the layer-1
+// activation (196 KB/patch) and the depthwise output (2 x 98 KB/patch of fp16 planes) never leave the SM:
+//   1. stage 13 log-mel rows in smem          2. layer-1 tile 6 x 34 x 32 (1-pixel halo, zero outside the image)
+//   3. depthwise from smem -> hi/lo fp16 straight into the SWIZZLE_128B A tile        4. one thread issues the
+//   tcgen05 MMAs (K = 32: two k-steps x 3 products) against the resident weight tile (TMA, loaded once per CTA)
+//   5. all 16 warps drain TMEM (32 rows x 16 columns each) through a smem transpose into coalesced stores.
+// No warp specialisation: two such CTAs share an SM and overlap each other's phases.
+constexpr int kL12Threads = 512;
+constexpr int kL12Rows = 4;                                   // image rows per tile (x 32 columns = 128 pixels)
+constexpr int kL12TileH = kL12Rows + 2, kL12TileW = 34;
+constexpr int kL12LmRows = 2 * kL12TileH + 1, kL12LmStride = 66;
+constexpr int kL12EpiStride = 20;                             // floats per staged row (16 + 4 pad)
+constexpr int kL12ABytes = 2 * kBM * kBK * 2;                 // A hi + lo
+constexpr int kL12BBytes = 2 * 64 * kBK * 2;                  // W hi + lo (64 x 64 box, columns 32..63 are OOB zeros)
+constexpr int kL12ScratchBytes = 16 * 32 * kL12EpiStride * 4; // epilogue staging; aliases the layer-1 tile + log-mel rows
+static_assert(kL12ScratchBytes >= (kL12TileH * kL12TileW * 32 + kL12LmRows * kL12LmStride) * 4, "scratch too small");
+constexpr int kL12SmemBytes = kL12ABytes + kL12BBytes + kL12ScratchBytes + 2 * (9 * 32 + 32) * 4 + 64 + 1024;
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(kL12Threads, 2)
+l12_fused_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                 const float* __restrict__ logmel, int hop_frames, int P, const float* __restrict__ w1,
+                 const float* __restrict__ b1, const float* __restrict__ dw_w, const float* __restrict__ dw_b,
+                 const float* __restrict__ bias, float* __restrict__ C, float out_scale) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* a_hi = smem;
+    unsigned char* a_lo = smem + kBM * kBK * 2;
+    unsigned char* b_hi = smem + kL12ABytes;
+    unsigned char* b_lo = b_hi + 64 * kBK * 2;
+    float* scratch = reinterpret_cast<float*>(smem + kL12ABytes + kL12BBytes);
+    float* c1 = scratch;                                       // [6][34][32]
+    float* lm = c1 + kL12TileH * kL12TileW * 32;               // [13][66]
+    float* sw = reinterpret_cast<float*>(smem + kL12ABytes + kL12BBytes + kL12ScratchBytes);   // [9][32]
+    float* sb = sw + 9 * 32;                                   // [32]
+    float* skw = sb + 32;                                      // depthwise taps [9][32]
+    float* skb = skw + 9 * 32;                                 // depthwise bias [32]
+    uint64_t* b_bar = reinterpret_cast<uint64_t*>(skb + 32);
+    uint64_t* mma_bar = b_bar + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cg = tid & 7;
+    for (int i = tid; i < 9 * 32; i += kL12Threads) { sw[i] = w1[i]; skw[i] = dw_w[i]; }
+    if (tid < 32) { sb[tid] = b1[tid]; skb[tid] = dw_b[tid]; }
+    if (tid == 0) {
+        tma_prefetch_desc(&map_b_hi);
+        mbar_init(b_bar, 1);
+        mbar_init(mma_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<64>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) {                                            // weights: once per CTA
+        mbar_arrive_expect_tx(b_bar, NSPLIT > 1 ? kL12BBytes : kL12BBytes / 2);
+        tma_load_2d(b_hi, &map_b_hi, b_bar, 0, 0);
+        if (NSPLIT > 1) tma_load_2d(b_lo, &map_b_lo, b_bar, 0, 0);
+    }
+    constexpr uint32_t idesc = umma_idesc_f16(kBM, 64);
+    uint32_t mma_phase = 0;
+    bool b_ready = false;
+
+    const unsigned tiles_per_patch = 48 / kL12Rows;           // 12
+    const unsigned n_tiles = static_cast<unsigned>(P) * tiles_per_patch;
+    for (unsigned t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const long long p = t / tiles_per_patch;
+        const int r0 = static_cast<int>(t - static_cast<unsigned>(p) * tiles_per_patch) * kL12Rows;
+        const float* in = logmel + p * hop_frames * kMel;
+        // ---- 1. log-mel rows 2*(r0-1) .. +12, columns 0..64
+        const int lm_row0 = 2 * (r0 - 1);
+        for (int i = tid; i < kL12LmRows * 65; i += kL12Threads) {
+            const int rr = i / 65, cc = i - rr * 65;
+            const int gr = lm_row0 + rr;
+            lm[rr * kL12LmStride + cc] = (gr >= 0 && gr < kPatchFrames && cc < kMel) ? __ldg(in + gr * kMel + cc) : 0.f;
+        }
+        __syncthreads();
+        // ---- 2. layer-1 tile with halo
+        {
+            float4 w1r[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) w1r[i] = *reinterpret_cast<const float4*>(sw + i * 32 + cg * 4);
+            const float4 b1r = *reinterpret_cast<const float4*>(sb + cg * 4);
+            for (int i = tid; i < kL12TileH * kL12TileW * 8; i += kL12Threads) {
+                const int px = i >> 3;
+                const int tr = px / kL12TileW, tc = px - tr * kL12TileW;
+                const int ir = r0 - 1 + tr, ic = tc - 1;
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ir >= 0 && ir < 48 && ic >= 0 && ic < 32) {
+                    a = b1r;
+                    const float* l0 = lm + (2 * tr) * kL12LmStride + 2 * ic;
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw) {
+                            const float v = l0[kh * kL12LmStride + kw];
+                            const float4 wk = w1r[kh * 3 + kw];
+                            a.x = fmaf(v, wk.x, a.x);
+                            a.y = fmaf(v, wk.y, a.y);
+                            a.z = fmaf(v, wk.z, a.z);
+                            a.w = fmaf(v, wk.w, a.w);
+                        }
+                    }
+                    a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+                }
+                *reinterpret_cast<float4*>(c1 + px * 32 + cg * 4) = a;
+            }
+        }
+        __syncthreads();
+        // ---- 3. depthwise: thread = (row 0..3, strip of 2 columns 0..15, channel quad) -> A tile rows
+        {
+            const int ws = (tid >> 3) & 15, orow = tid >> 7;
+            const float4 bdw = *reinterpret_cast<const float4*>(skb + cg * 4);
+            float4 acc[2] = {bdw, bdw};
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+                const float* rowp = c1 + ((orow + kh) * kL12TileW + ws * 2) * 32 + cg * 4;
+                float4 v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(rowp + j * 32);
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(skw + (kh * 3 + kw) * 32 + cg * 4);
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const float4 x = v[r + kw];
+                        acc[r].x = fmaf(x.x, w4.x, acc[r].x);
+                        acc[r].y = fmaf(x.y, w4.y, acc[r].y);
+                        acc[r].z = fmaf(x.z, w4.z, acc[r].z);
+                        acc[r].w = fmaf(x.w, w4.w, acc[r].w);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                float4 a = acc[r];
+                a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+                const int row = orow * 32 + ws * 2 + r;
+                const uint32_t off = static_cast<uint32_t>((row >> 3) * 1024 + (row & 7) * 128 +
+                                                           ((((cg >> 1) ^ (row & 7))) << 4) + ((cg & 1) << 3));
+                const __half h0 = __float2half_rn(a.x), h1 = __float2half_rn(a.y);
+                const __half h2 = __float2half_rn(a.z), h3 = __float2half_rn(a.w);
+                __half2 hp[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
+                *reinterpret_cast<uint2*>(a_hi + off) = *reinterpret_cast<uint2*>(hp);
+                if (NSPLIT > 1) {
+                    __half2 lp[2] = {__halves2half2(__float2half_rn(a.x - __half2float(h0)),
+                                                    __float2half_rn(a.y - __half2float(h1))),
+                                     __halves2half2(__float2half_rn(a.z - __half2float(h2)),
+                                                    __float2half_rn(a.w - __half2float(h3)))};
+                    *reinterpret_cast<uint2*>(a_lo + off) = *reinterpret_cast<uint2*>(lp);
+                }
+            }
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        // ---- 4. MMA: K = 32 -> k-steps 0 and 1 only
+        if (tid == 0) {
+            if (!b_ready) { mbar_wait(b_bar, 0); }
+            tc_fence_after();
+            const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const uint32_t koff = static_cast<uint32_t>(k) * 32u;
+                umma_f16_ss(tmem_base, umma_desc_k128(ah + koff), umma_desc_k128(bh + koff), idesc, k != 0 ? 1u : 0u);
+                if (NSPLIT > 1) {
+                    umma_f16_ss(tmem_base, umma_desc_k128(al + koff), umma_desc_k128(bh + koff), idesc, 1u);
+                    umma_f16_ss(tmem_base, umma_desc_k128(ah + koff), umma_desc_k128(bl + koff), idesc, 1u);
+                }
+            }
+            umma_commit(mma_bar);
+        }
+        b_ready = true;
+        mbar_wait(mma_bar, mma_phase);
+        mma_phase ^= 1;
+        tc_fence_after();
+        // ---- 5. epilogue: warp = (TMEM lane quad q, 16-column group)
+        {
+            const int q = warp & 3, colgrp = warp >> 2;
+            float* stg = scratch + warp * 32 * kL12EpiStride;     // aliases c1/lm: every thread is past phase 3
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(colgrp * 16), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + colgrp * 16 + j));
+                float4 o;
+                o.x = fmaxf(fmaf(__uint_as_float(r[j + 0]), out_scale, bv.x), 0.f);
+                o.y = fmaxf(fmaf(__uint_as_float(r[j + 1]), out_scale, bv.y), 0.f);
+                o.z = fmaxf(fmaf(__uint_as_float(r[j + 2]), out_scale, bv.z), 0.f);
+                o.w = fmaxf(fmaf(__uint_as_float(r[j + 3]), out_scale, bv.w), 0.f);
+                *reinterpret_cast<float4*>(stg + lane * kL12EpiStride + j) = o;
+            }
+            __syncwarp();
+            const long long m0 = static_cast<long long>(t) * kBM + q * 32;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int rl = i * 8 + (lane >> 2);
+                const float4 o = *reinterpret_cast<const float4*>(stg + rl * kL12EpiStride + (lane & 3) * 4);
+                *reinterpret_cast<float4*>(C + (m0 + rl) * 64 + colgrp * 16 + (lane & 3) * 4) = o;
+            }
+        }
+        tc_fence_before();
+        __syncthreads();                                       // TMEM drained, scratch free for the next tile
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<64>(tmem_base);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -566,6 +786,8 @@ cudaError_t pw_gemm_init_device() {
     if ((e = set_attr<64, 3>()) != cudaSuccess) return e;
     if ((e = set_attr<128, 3>()) != cudaSuccess) return e;
     if ((e = set_attr<256, 3>()) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(l12_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kL12SmemBytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(l12_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kL12SmemBytes)) != cudaSuccess) return e;
 #define BD_FUSED_ATTR(BN)                                                           \
     if ((e = set_attr_fused<BN, 1, 1>()) != cudaSuccess) return e;                  \
     if ((e = set_attr_fused<BN, 1, 2>()) != cudaSuccess) return e;                  \
@@ -578,11 +800,29 @@ cudaError_t pw_gemm_init_device() {
     return cudaSuccess;
 }
 
+cudaError_t launch_l12_fused(const PwGemmPlan& p, const float* logmel, int hop_frames, int P, const float* w1,
+                             const float* b1, const float* dw_w, const float* dw_b, const float* bias, float* C,
+                             int num_sms, cudaStream_t stream) {
+    if (P <= 0) return cudaSuccess;
+    if (p.N != 64 || p.K != 32 || p.block_n != 64) return cudaErrorInvalidValue;
+    const long long tiles = static_cast<long long>(P) * (48 / kL12Rows);
+    if (tiles >= (1LL << 31)) return cudaErrorInvalidValue;
+    const int grid = static_cast<int>(tiles < 2LL * num_sms ? tiles : 2LL * num_sms);
+    if (p.nsplit == 1)
+        l12_fused_kernel<1><<<grid, kL12Threads, kL12SmemBytes, stream>>>(p.b_hi, p.b_lo, logmel, hop_frames, P, w1, b1,
+                                                                          dw_w, dw_b, bias, C, p.out_scale);
+    else
+        l12_fused_kernel<3><<<grid, kL12Threads, kL12SmemBytes, stream>>>(p.b_hi, p.b_lo, logmel, hop_frames, P, w1, b1,
+                                                                          dw_w, dw_b, bias, C, p.out_scale);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_sep_fused(const PwGemmPlan& p, const float* X, const float* dw_w, const float* dw_b,
                              const float* bias, float* C, int P, int H, int W, int stride, int num_sms,
                              cudaStream_t stream) {
     if (P <= 0) return cudaSuccess;
     if ((stride != 1 && stride != 2) || (W / stride) % 4 != 0 || p.K % 4 != 0) return cudaErrorInvalidValue;
+    if (((W / stride) & (W / stride - 1)) != 0) return cudaErrorInvalidValue;      // producers index with shifts
 #define BD_FUSED(BN, NS)                                                                                         \
     return stride == 1 ? launch_fused_t<BN, NS, 1>(p, X, dw_w, dw_b, bias, C, P, H, W, num_sms, stream)          \
                        : launch_fused_t<BN, NS, 2>(p, X, dw_w, dw_b, bias, C, P, H, W, num_sms, stream)

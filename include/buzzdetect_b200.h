@@ -37,6 +37,8 @@ extern "C" {
 /* precision of the pointwise (1x1) convolutions */
 #define BD_PRECISION_FP32_SIMT 0   /* float32 FMA on CUDA cores (on-device reference mode)              */
 #define BD_PRECISION_FP16X1 1      /* tcgen05, fp16 operands, fp32 accumulate: 1 MMA  (~5e-4 relative)   */
+#define BD_FUSE_CONV1_DW2 (1 << 16)   /* fuse_mask bit: layer 1 + layer-2 depthwise in one kernel              */
+#define BD_FUSE_L12 (1 << 17)         /* fuse_mask bit: layers 1 and 2 entirely in one kernel (tensor-core modes) */
 #define BD_PRECISION_FP16X3 3      /* tcgen05, hi/lo fp16 split, 3 MMAs: float32-equivalent (default)    */
 
 typedef struct bd_engine bd_engine;
@@ -66,8 +68,10 @@ typedef struct bd_config {
     int32_t late_patches;          /* patches per sub-batch for layer 7 pointwise..head     (0 = default)   */
     int32_t use_graph;             /* 1 = capture and replay CUDA graphs per (n_samples, hop)               */
     int32_t n_slots;               /* in-flight host chunks for bd_submit_host (1..4, 0 = 2)                */
-    int32_t fuse_mask;             /* bit (L-2): run separable layer L as ONE fused depthwise+pointwise kernel;
-                                      -1 = default (layer 3 only).  Ignored in BD_PRECISION_FP32_SIMT.         */
+    int32_t fuse_mask;             /* bit (L-2): run separable layer L as ONE fused depthwise+pointwise kernel
+                                      (ignored in BD_PRECISION_FP32_SIMT); BD_FUSE_CONV1_DW2: layer 1 + layer-2
+                                      depthwise in one kernel; BD_FUSE_L12: layers 1+2 in one kernel.
+                                      -1 = default (layer 3 | BD_FUSE_CONV1_DW2).                                   */
 } bd_config;
 
 int32_t bd_abi_version(void);
