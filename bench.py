@@ -68,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -189,14 +189,16 @@ def run_ours(args, rank, world, local):
     torch.cuda.synchronize()
 
     # ---------------- device-resident throughput ("value")
+    # nvidia-smi needs ~100 ms to start reporting, longer than one timed region, so the sampler runs from the warm-up
+    # of the device-resident leg to the end of the timed end-to-end leg: every sample is taken under load.
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         eng.predict_device_ptr(d_x.data_ptr(), n, HOP_FRAMES, d_act.data_ptr())
     if use_dist:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(dev)
-    if rank == 0:
-        sampler.start()
     l0 = eng.launch_count
     ms = eng.bench_device_ptr(d_x.data_ptr(), n, HOP_FRAMES, d_act.data_ptr(), args.steps)
     torch.cuda.synchronize()
@@ -206,7 +208,6 @@ def run_ours(args, rank, world, local):
         dist.barrier()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
     value = world * hours_per_step * args.steps / (ms_max / 1000.0)
 
     # ---------------- end to end through the C ABI with host buffers
@@ -246,48 +247,75 @@ def run_ours(args, rank, world, local):
         dist.barrier()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * hours_per_step * args.steps / float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
     d2h_bytes = sum(o.numel() * 4 for o in outs)
 
-    # ---------------- per-stage device times (one extra un-graphed pass, events around every launch)
+    # ---------------- per-kernel-family device times (one extra un-graphed pass, CUDA events around every launch)
     prof = eng.profile_device_ptr(d_x.data_ptr(), n, HOP_FRAMES)
     peaks = measured_peaks()
-    pw_ms = prof["pointwise"]["ms"]
-    pw_l = max(prof["pointwise"]["launches"], 1)
-    pw_tflops = PW_FLOP_PER_PATCH * P / (pw_ms / 1000.0) / 1e12 if pw_ms > 0 else 0.0
-    mma_factor = {"fp16x3": 3, "fp16": 1, "fp32": 0}[args.precision]
-    stages = {}
-    for name, bytes_pp in (("frontend", FRONTEND_BYTES_PER_PATCH), ("depthwise", DW_BYTES_PER_PATCH)):
-        m = prof[name]["ms"]
-        gbs = bytes_pp * P / (m / 1000.0) / 1e9 if m > 0 else 0.0
-        stages[name] = {"ms": m, "launches": prof[name]["launches"], "achieved_gbs": gbs,
-                        "frac_hbm": gbs / peaks["hbm_gbs"]}
-    stages["pointwise"] = {"ms": pw_ms, "launches": prof["pointwise"]["launches"], "achieved_tflops": pw_tflops,
-                           "executed_mma_tflops": pw_tflops * mma_factor}
-    stages["conv1"] = prof["conv1"]
-    stages["pool_head"] = prof["pool_head"]
-    total_prof_ms = sum(prof[k]["ms"] for k in ("frontend", "conv1", "depthwise", "pointwise", "pool_head"))
-    # per-layer view: algorithmic bytes (fp32 in + out) for depthwise, flops for pointwise
     from buzzdetect_b200.weights import LAYERS
+    mma_factor = {"fp16x3": 3, "fp16": 1, "fp32": 0}[args.precision]
     per_layer = {}
+    fam = {"pw_gemm_kernel": {"ms": 0.0, "launches": 0, "flop": 0.0, "bytes": 0.0},
+           "pw_gemm_kernel[layers 7-14]": {"ms": 0.0, "launches": 0, "flop": 0.0, "bytes": 0.0},
+           "sep_fused_kernel": {"ms": 0.0, "launches": 0, "flop": 0.0, "bytes": 0.0},
+           "depthwise_kernel": {"ms": 0.0, "launches": 0, "flop": 0.0, "bytes": 0.0}}
     for i, (kind, stride, cin, cout, H, W) in enumerate(LAYERS[1:]):
         v = prof["layers"][f"L{i + 2}"]
         ho, wo = H // stride, W // stride
-        dw_bytes = (H * W * cin + ho * wo * cin) * 4 * P
+        dw_bytes = (H * W * cin + ho * wo * cin) * 4.0 * P              # fp32 in + (hi+lo fp16 = 4 B) out
         pw_flop = 2.0 * ho * wo * cin * cout * P
-        pw_bytes = (ho * wo * cin + ho * wo * cout) * 4 * P
+        pw_bytes = (ho * wo * cin + ho * wo * cout) * 4.0 * P
+        fused = v["dw_launches"] == 0 and v["pw_launches"] > 0 and i + 2 != 2
         per_layer[f"L{i + 2}"] = {
-            "dw_ms": round(v["dw_ms"], 4), "dw_gbs": round(dw_bytes / max(v["dw_ms"], 1e-9) / 1e6, 1),
-            "pw_ms": round(v["pw_ms"], 4), "pw_tflops": round(pw_flop / max(v["pw_ms"], 1e-9) / 1e9, 1),
-            "pw_gbs": round(pw_bytes / max(v["pw_ms"], 1e-9) / 1e6, 1), "K": cin, "N": cout, "M": ho * wo * P}
-    roofline = {
-        "bound": "tensor", "kernel": "pw_gemm_kernel (13 pointwise 1x1 convs)",
-        "achieved": pw_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-        "frac": pw_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
-        "peak_source": peaks["source"] + " bf16 sustained (kernel timed inside a long step)",
-        "flop_per_launch": PW_FLOP_PER_PATCH * P / pw_l, "avg_launch_ms": pw_ms / pw_l,
-        "share_of_step": pw_ms / total_prof_ms if total_prof_ms > 0 else None,
-        "executed_mma_factor": mma_factor,
-    }
+            "dw_ms": round(v["dw_ms"], 4), "dw_gbs": round(dw_bytes / max(v["dw_ms"], 1e-9) / 1e6, 1) if v["dw_ms"] else None,
+            "pw_ms": round(v["pw_ms"], 4), "pw_tflops": round(pw_flop / max(v["pw_ms"], 1e-9) / 1e9, 1) if v["pw_ms"] else None,
+            "fused": fused, "K": cin, "N": cout, "M": ho * wo * P}
+        if v["dw_launches"]:
+            f = fam["depthwise_kernel"]
+            f["ms"] += v["dw_ms"]; f["launches"] += v["dw_launches"]; f["bytes"] += dw_bytes
+        if v["pw_launches"]:
+            names = ["sep_fused_kernel"] if fused else (["pw_gemm_kernel"] + (["pw_gemm_kernel[layers 7-14]"] if i + 2 >= 7 else []))
+            for nm in names:
+                f = fam[nm]
+                f["ms"] += v["pw_ms"]; f["launches"] += v["pw_launches"]; f["flop"] += pw_flop
+                f["bytes"] += ((H * W * cin + ho * wo * cout) * 4.0 * P) if fused else pw_bytes
+    c1_bytes = (96 * 64 + 48 * 32 * 32) * 4.0 * P
+    fam["conv1_dw2_kernel"] = {"ms": prof["conv1"]["ms"], "launches": prof["conv1"]["launches"], "flop": 0.0,
+                               "bytes": c1_bytes}
+    fam["logmel_kernel"] = {"ms": prof["frontend"]["ms"], "launches": prof["frontend"]["launches"], "flop": 0.0,
+                            "bytes": FRONTEND_BYTES_PER_PATCH * float(P)}
+    total_prof_ms = sum(prof[k]["ms"] for k in ("frontend", "conv1", "depthwise", "pointwise", "pool_head"))
+    traffic_tab = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic_tab = json.load(f)
+    rooflines = {}
+    for nm, f in fam.items():
+        if f["ms"] <= 0:
+            continue
+        tens = nm.startswith("pw_gemm")
+        ach = (f["flop"] / (f["ms"] / 1e3) / 1e12) if tens else (f["bytes"] / (f["ms"] / 1e3) / 1e9)
+        peak = peaks["bf16_tflops_sustained"] if tens else peaks["hbm_gbs"]
+        rooflines[nm] = {"bound": "tensor" if tens else "hbm", "achieved": ach, "peak": peak,
+                         "unit": "TFLOP/s" if tens else "GB/s", "frac": ach / peak, "ms": f["ms"],
+                         "launches": f["launches"], "share_of_step": f["ms"] / total_prof_ms,
+                         "algorithmic_per_launch": (f["flop"] if tens else f["bytes"]) / max(f["launches"], 1),
+                         "avg_launch_ms": f["ms"] / max(f["launches"], 1),
+                         "traffic": traffic_tab.get(nm, {}).get("dram_bytes_per_launch")}
+        if tens:
+            rooflines[nm]["executed_mma_factor"] = mma_factor
+            rooflines[nm]["hbm_gbs"] = f["bytes"] / (f["ms"] / 1e3) / 1e9
+    dominant = max((k for k in rooflines if "[" not in k), key=lambda k: rooflines[k]["ms"])
+    roofline = dict(rooflines[dominant])
+    roofline["kernel"] = dominant
+    roofline["peak_source"] = peaks["source"] + (" bf16 sustained (kernel timed inside a long step)"
+                                                if roofline["bound"] == "tensor" else " copy bandwidth")
+    roofline["note"] = ("algorithmic flops; fp16x3 executes 3 MMAs per algorithmic MMA, and layers 2-6 of this kernel "
+                        "family are HBM-bound (K <= 256): see rooflines['pw_gemm_kernel[layers 7-14]'] for the "
+                        "tensor-bound subset") if roofline["bound"] == "tensor" else "algorithmic bytes (fp32 in + out)"
+    stages = {k: prof[k] for k in ("frontend", "conv1", "depthwise", "pointwise", "pool_head")}
 
     if rank == 0:
         cpu_v, cpu_dt, cores, sample = time_oracle(steps=2, warmup=1) if (world == 1 and not args.no_cpu) else (None,) * 4
@@ -308,6 +336,7 @@ def run_ours(args, rank, world, local):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
+            "rooflines": rooflines,
             "stages": stages,
             "layers": per_layer,
             "whole_path_tflops": TOTAL_FLOP_PER_PATCH * P * world * args.steps / (ms_max / 1000.0) / 1e12,

@@ -58,6 +58,8 @@ SIGNATURES = {
     "bd_predict_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, _i64p]),
     "bd_submit_host": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                    _i64p]),
+    "bd_submit_pcm_host": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32,
+                                       C.c_int32, C.c_void_p, C.c_void_p, _i64p]),
     "bd_wait": (C.c_int32, [C.c_void_p, C.c_int32]),
     "bd_synchronize": (C.c_int32, [C.c_void_p]),
     "bd_profile_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, _f32p, _i64p]),
@@ -224,6 +226,31 @@ class Engine:
         self._check(self._lib.bd_submit_host(self._h, slot, host_ptr, n, hop_frames, act_ptr, emb_ptr, C.byref(npat)),
                     "bd_submit_host")
         return npat.value
+
+    def submit_pcm_ptr(self, slot: int, pcm_ptr: int, fmt: int, channels: int, n_frames: int, src_rate: int,
+                       hop_frames: int, act_ptr: int, emb_ptr: int | None = None) -> int:
+        """Raw decoded PCM in (int16/float32, interleaved), activations out; downmix + resample run on the GPU."""
+        npat = C.c_int64()
+        self._check(self._lib.bd_submit_pcm_host(self._h, slot, pcm_ptr, fmt, channels, n_frames, src_rate, hop_frames,
+                                                 act_ptr, emb_ptr, C.byref(npat)), "bd_submit_pcm_host")
+        return npat.value
+
+    def predict_pcm(self, pcm: np.ndarray, src_rate: int, hop_frames: int = 96) -> np.ndarray:
+        """[n] or [n, channels] int16/float32 at src_rate -> [P, n_classes] (synchronous convenience wrapper)."""
+        a = np.asarray(pcm)
+        fmt = 1 if a.dtype == np.int16 else 0
+        if fmt == 0:
+            a = a.astype(np.float32, copy=False)
+        a = np.ascontiguousarray(a)
+        ch = 1 if a.ndim == 1 else a.shape[1]
+        n_out = int(self._lib.bd_resample_out_len(a.shape[0], src_rate))
+        _, _, P = frames_for(n_out, hop_frames)
+        act = np.empty((P, self.n_classes), dtype=np.float32)
+        self.wait(0)
+        got = self.submit_pcm_ptr(0, a.ctypes.data, fmt, ch, a.shape[0], src_rate, hop_frames, act.ctypes.data)
+        self.wait(0)
+        assert got == P
+        return act
 
     def wait(self, slot: int):
         self._check(self._lib.bd_wait(self._h, slot), "bd_wait")

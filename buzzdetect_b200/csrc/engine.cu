@@ -42,6 +42,8 @@ struct LayerDev {
 struct Slot {
     float* d_in = nullptr;
     int64_t in_cap = 0;
+    unsigned char* d_pcm = nullptr;  // raw decoded chunk (bd_submit_pcm_host)
+    int64_t pcm_cap = 0;
     float* d_act = nullptr;
     float* d_emb = nullptr;
     int64_t out_cap = 0;            // patches
@@ -384,7 +386,7 @@ void bd_engine_destroy(bd_engine* e) {
     cudaDeviceSynchronize();
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
     for (auto& s : e->slots) {
-        cudaFree(s.d_in); cudaFree(s.d_act); cudaFree(s.d_emb);
+        cudaFree(s.d_in); cudaFree(s.d_pcm); cudaFree(s.d_act); cudaFree(s.d_emb);
         if (s.ev_in) cudaEventDestroy(s.ev_in);
         if (s.ev_comp) cudaEventDestroy(s.ev_comp);
         if (s.ev_out) cudaEventDestroy(s.ev_out);
@@ -773,6 +775,51 @@ int32_t bd_resample_device(bd_engine* e, const void* d_in, int32_t fmt, int32_t 
                                 e->s_compute));
     e->launch_count++;
     BD_CHECK(e, cudaStreamSynchronize(e->s_compute));
+    return 0;
+}
+
+int32_t bd_submit_pcm_host(bd_engine* e, int32_t slot, const void* pcm, int32_t fmt, int32_t channels,
+                           int64_t n_frames, int32_t src_rate, int32_t hop_frames, float* act, float* emb,
+                           int64_t* n_patches) {
+    if (!e) return 1;
+    if (slot < 0 || slot >= static_cast<int>(e->slots.size())) return fail(e, "slot out of range");
+    if ((fmt != 0 && fmt != 1) || channels < 1 || channels > 8 || src_rate < 1000 || n_frames < 0)
+        return fail(e, "bad PCM arguments");
+    if (hop_frames < 1 || hop_frames > kPatchFrames) return fail(e, "bad hop_frames");
+    BD_CHECK(e, cudaSetDevice(e->device));
+    Slot& s = e->slots[slot];
+    if (s.busy) return fail(e, "slot still in flight: call bd_wait first");
+    const int64_t n = bd_resample_out_len(n_frames, src_rate);
+    int64_t P = 0;
+    frames_for(n, hop_frames, nullptr, nullptr, &P);
+    if (n_patches) *n_patches = P;
+    if (P == 0) return 0;
+    if ((n_frames > 0 && !pcm) || !act) return fail(e, "null host buffer");
+    if (ensure_slot(e, s, n, P)) return 1;
+    const int64_t pcm_bytes = n_frames * channels * (fmt == 0 ? 4 : 2);
+    if (pcm_bytes > s.pcm_cap) {
+        if (s.d_pcm) cudaFree(s.d_pcm);
+        s.d_pcm = nullptr;
+        const int64_t cap = ((pcm_bytes + 65535) / 65536) * 65536;
+        BD_CHECK(e, cudaMalloc(&s.d_pcm, cap));
+        s.pcm_cap = cap;
+    }
+    bd_engine::Resampler ident{1, 1, 1, nullptr};
+    bd_engine::Resampler* r = &ident;
+    if (src_rate != 16000 && get_resampler(e, src_rate, &r)) return 1;
+    if (n_frames > 0) BD_CHECK(e, cudaMemcpyAsync(s.d_pcm, pcm, pcm_bytes, cudaMemcpyHostToDevice, e->s_in));
+    BD_CHECK(e, cudaEventRecord(s.ev_in, e->s_in));
+    BD_CHECK(e, cudaStreamWaitEvent(e->s_compute, s.ev_in, 0));
+    BD_CHECK(e, launch_resample(s.d_pcm, fmt, channels, n_frames, r->up, r->down, r->d_taps, r->taps_per_phase, s.d_in, n,
+                                e->s_compute));
+    e->launch_count++;
+    if (run_chunk(e, s.d_in, n, hop_frames, s.d_act, emb ? s.d_emb : nullptr, P)) return 1;
+    BD_CHECK(e, cudaEventRecord(s.ev_comp, e->s_compute));
+    BD_CHECK(e, cudaStreamWaitEvent(e->s_out, s.ev_comp, 0));
+    BD_CHECK(e, cudaMemcpyAsync(act, s.d_act, P * e->n_classes * sizeof(float), cudaMemcpyDeviceToHost, e->s_out));
+    if (emb) BD_CHECK(e, cudaMemcpyAsync(emb, s.d_emb, P * kEmb * sizeof(float), cudaMemcpyDeviceToHost, e->s_out));
+    BD_CHECK(e, cudaEventRecord(s.ev_out, e->s_out));
+    s.busy = true;
     return 0;
 }
 

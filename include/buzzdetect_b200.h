@@ -92,6 +92,12 @@ int32_t bd_predict_device(bd_engine* e, const float* d_samples, int64_t n, int32
                           float* d_emb, int64_t* n_patches);
 int32_t bd_submit_host(bd_engine* e, int32_t slot, const float* samples, int64_t n, int32_t hop_frames, float* act,
                        float* emb, int64_t* n_patches);
+/* Same as bd_submit_host, for a chunk still in its decoded form: interleaved PCM [n_frames, channels] at src_rate
+ * (fmt 0 float32, 1 int16).  Downmix + resample run on the device, so only the raw PCM crosses PCIe
+ * (src/stream/worker.py:110-129 + src/inference/worker.py:72 in one call). */
+int32_t bd_submit_pcm_host(bd_engine* e, int32_t slot, const void* pcm, int32_t fmt, int32_t channels,
+                           int64_t n_frames, int32_t src_rate, int32_t hop_frames, float* act, float* emb,
+                           int64_t* n_patches);
 int32_t bd_wait(bd_engine* e, int32_t slot);
 int32_t bd_synchronize(bd_engine* e);
 
