@@ -520,12 +520,14 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
     e->H_early_plane_bytes = sizeof(__half) * h_early * e->S1 + plane_pad;
     BD_CREATE(cudaMalloc(&e->d_H_early, sizeof(float) * h_early * e->S1 + plane_pad));
     BD_CREATE(cudaMemset(e->d_H_early, 0, sizeof(float) * h_early * e->S1 + plane_pad));
-    BD_CREATE(cudaMalloc(&e->d_F_early2, sizeof(float) * f_early * e->S1));
     BD_CREATE(cudaMalloc(&e->d_F_late, sizeof(float) * f_late * e->S2));
-    BD_CREATE(cudaMalloc(&e->d_F_late2, sizeof(float) * f_late * e->S2));
     e->H_late_plane_bytes = sizeof(__half) * h_late * e->S2 + plane_pad;
     BD_CREATE(cudaMalloc(&e->d_H_late, sizeof(float) * h_late * e->S2 + plane_pad));
     BD_CREATE(cudaMemset(e->d_H_late, 0, sizeof(float) * h_late * e->S2 + plane_pad));
+
+    // ping-pong partners, only touched by fused separable blocks
+    BD_CREATE(cudaMalloc(&e->d_F_early2, sizeof(float) * f_early * e->S1));
+    BD_CREATE(cudaMalloc(&e->d_F_late2, sizeof(float) * f_late * e->S2));
 
     // ---- tensor-core operands: weight planes + TMA descriptors
     if (e->precision != BD_PRECISION_FP32_SIMT) {

@@ -228,3 +228,45 @@ def test_device_resident_entry_point(engines):
     assert all(prof[k]["ms"] > 0 for k in ("frontend", "conv1", "depthwise", "pointwise", "pool_head"))
     assert [v["pw_launches"] for v in prof["layers"].values()] == [1] * 13
     assert [v["dw_launches"] for v in prof["layers"].values()] == [0, 0] + [1] * 11
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_prefix_and_padding_properties(engines):
+    """BASELINE configs[1] size (1 h, 3750 patches), default sub-batches: frame p depends only on samples
+    [15360 p, 15360 p + 15600), so any prefix reproduces the same rows bit for bit, and explicit zero padding up to
+    the padded length changes nothing."""
+    e = engines("fp16x3")
+    base = O.synth_audio(60 * 16000, seed=77)
+    x = np.tile(base, 60)
+    full = e.predict(x, 96)
+    assert full.shape == (3750, 13) and np.isfinite(full).all()
+    for k in (1, 100, 1025, 3000):
+        part = e.predict(x[:15360 * k + 240], 96)
+        assert part.shape[0] == k and np.array_equal(part, full[:k]), k
+    ragged = x[:16000 * 33 + 1234]
+    npad, _, P = O.frame_counts(len(ragged), 96)
+    a = e.predict(ragged, 96)
+    b = e.predict(np.concatenate([ragged, np.zeros(npad - len(ragged), np.float32)]), 96)
+    assert a.shape[0] == P and np.array_equal(a, b)
+
+
+def test_day_long_single_call_has_no_index_overflow(engines):
+    """configs[2] scale in ONE call: 24 h = 1.3824e9 samples (5.5 GB, byte offsets beyond 2**32).  The signal repeats
+    every 15360 samples, so all 90000 frames but the last (which sees the zero padding) must be bit-identical."""
+    import torch
+    e = engines("fp16x3")
+    period = torch.from_numpy(O.synth_audio(15360, seed=5)).cuda()
+    n = 24 * 3600 * 16000
+    x = period.repeat(n // 15360)
+    assert x.numel() == n
+    P = O.frame_counts(n, 96)[2]
+    assert P == 90000
+    act = torch.empty((P, 13), dtype=torch.float32, device="cuda")
+    got = e.predict_device_ptr(x.data_ptr(), n, 96, act.data_ptr())
+    assert got == P
+    a = act.cpu().numpy()
+    assert np.isfinite(a).all()
+    assert (a[:-1] == a[0]).all()
+    assert not np.array_equal(a[-1], a[0])          # the last frame ends in 240 samples of padding
+    del x, act
+    torch.cuda.empty_cache()
