@@ -89,6 +89,26 @@ cudaError_t launch_sep_fused(const PwGemmPlan& plan, const float* X, const float
                              const float* bias, float* C, int P, int H, int W, int stride, int num_sms,
                              cudaStream_t stream);
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TensorMapEncodeFn tensor_map_encode_fn();
+
+// ---- sep_fused_sm100.cu  (fused separable block v3: TMA-staged depthwise input, see the file header)
+cudaError_t sep_fused3_init_device();
+bool sep_fused3_supported(int K, int N, int H, int W, int stride);
+// X: [P,H,W,K] float32 NHWC (16-byte aligned); C: [P*(H/stride)*(W/stride), N].  Uses the plan's weight maps.
+cudaError_t launch_sep_fused3(const PwGemmPlan& plan, const float* X, const float* dw_w, const float* dw_b,
+                              const float* bias, float* C, int P, int H, int W, int stride, int num_sms,
+                              cudaStream_t stream);
+
+// ---- l12_fused_sm100.cu  (layers 1 + 2, warp-specialised: conv1 warps -> stencil warps -> tcgen05 -> epilogue)
+cudaError_t l12_fused2_init_device();
+cudaError_t launch_l12_fused2(const PwGemmPlan& plan, const float* logmel, int hop_frames, int P, const float* w1,
+                              const float* b1, const float* dw_w, const float* dw_b, const float* bias, float* C,
+                              int num_sms, cudaStream_t stream);
+
 // ---- resample.cu
 cudaError_t launch_resample(const void* in, int in_fmt /*0 f32, 1 s16*/, int channels, long long n_in_frames,
                             int up, int down, const float* taps, int taps_per_phase, float* out, long long n_out,

@@ -37,6 +37,7 @@ struct LayerDev {
     PwGemmPlan plan;
     bool late = false;              // pointwise runs in the late phase
     bool fused = false;             // depthwise computed inside the pointwise GEMM (sep_fused_kernel)
+    bool fused_v3 = false;          // ... by sep_fused3_kernel (TMA-staged depthwise input)
 };
 
 struct Slot {
@@ -83,6 +84,7 @@ struct bd_engine {
     int first_late = 6;                   // index of the layer whose pointwise output starts the late phase (layer 7)
     bool fuse_conv1 = true;               // layer 1 + layer-2 depthwise in one kernel (conv1_dw2_kernel)
     bool fuse_l12 = true;                 // layers 1 + 2 entirely in one kernel (l12_fused_kernel, tensor-core modes)
+    bool l12_v2 = false;                  // ... using the warp-specialised l12_fused2_kernel
     const void* dbg_ptr = nullptr;        // bd_debug_stage: where the requested stage's output lives
     bool dbg_planes = false;
     size_t dbg_plane_off = 0;
@@ -191,8 +193,12 @@ int enqueue_chunk(bd_engine* e, const float* x, int64_t n, int hop_frames, float
     };
     auto fused = [&](int L, const float* in, int np, float* out) -> int {
         const LayerDev& l = e->layers[L];
-        BD_CHECK(e, launch_sep_fused(l.plan, in, l.dw_w, l.dw_b, l.b, out, np, l.d.h_in, l.d.w_in, l.d.stride, e->num_sms,
-                                     st));
+        if (l.fused_v3)
+            BD_CHECK(e, launch_sep_fused3(l.plan, in, l.dw_w, l.dw_b, l.b, out, np, l.d.h_in, l.d.w_in, l.d.stride,
+                                          e->num_sms, st));
+        else
+            BD_CHECK(e, launch_sep_fused(l.plan, in, l.dw_w, l.dw_b, l.b, out, np, l.d.h_in, l.d.w_in, l.d.stride,
+                                         e->num_sms, st));
         mark(e, CAT_PW + L - 1, st);
         if (stop_stage == 2 * L) { e->last_error = "stage is fused away (depthwise output stays in shared memory)"; return 1; }
         if (stop_at(2 * L + 1, out, false, 0)) return 2;
@@ -219,8 +225,12 @@ int enqueue_chunk(bd_engine* e, const float* x, int64_t n, int hop_frames, float
             if (e->fuse_l12) {
                 // layers 1 + 2 (conv1 -> depthwise -> pointwise) in one kernel: log-mel in, layer-2 output out
                 const LayerDev& l2 = e->layers[1];
-                BD_CHECK(e, launch_l12_fused(l2.plan, lm0, hop_frames, ns, l1.w, l1.b, l2.dw_w, l2.dw_b, l2.b, cur,
-                                             e->num_sms, st));
+                if (e->l12_v2)
+                    BD_CHECK(e, launch_l12_fused2(l2.plan, lm0, hop_frames, ns, l1.w, l1.b, l2.dw_w, l2.dw_b, l2.b, cur,
+                                                  e->num_sms, st));
+                else
+                    BD_CHECK(e, launch_l12_fused(l2.plan, lm0, hop_frames, ns, l1.w, l1.b, l2.dw_w, l2.dw_b, l2.b, cur,
+                                                 e->num_sms, st));
                 mark(e, CAT_CONV1, st);
                 if (stop_stage == 1 || stop_stage == 2) {
                     e->last_error = "stage is fused away (layers 1-2 run as one kernel)";
@@ -446,6 +456,8 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
     BD_CREATE(frontend_init_device());
     BD_CREATE(layers_init_device());
     if (e->precision != BD_PRECISION_FP32_SIMT) BD_CREATE(pw_gemm_init_device());
+    if (e->precision != BD_PRECISION_FP32_SIMT) BD_CREATE(sep_fused3_init_device());
+    if (e->precision != BD_PRECISION_FP32_SIMT) BD_CREATE(l12_fused2_init_device());
 
     // ---- weights
     BD_CREATE(cudaMalloc(&e->d_folded, w->folded_len * sizeof(float)));
@@ -483,10 +495,13 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
     // which separable blocks run fused: bit (L-2) for layer L.  Measured on B200 (profiles/fusion_r1.md): with the
     // current register-fed producers only layer 3 (stride 2, K=64) beats the two-kernel path, so that is the default.
     const int fuse_mask = e->precision == BD_PRECISION_FP32_SIMT ? 0 : (cfg->fuse_mask < 0 ? 0x2 : (cfg->fuse_mask & 0x1FFF));
+    const bool use_v3 = cfg->fuse_mask >= 0 && (cfg->fuse_mask & BD_FUSE_V3) != 0;
     e->fuse_conv1 = cfg->fuse_mask < 0 || (cfg->fuse_mask & BD_FUSE_CONV1_DW2) != 0;
     // measured (profiles/fusion_r1.md): the single-kernel layers-1+2 path is latency bound (1.18 ms per audio-hour vs
     // 0.44 + 0.70 for conv1_dw2 + pointwise), so it is opt-in
-    e->fuse_l12 = e->precision != BD_PRECISION_FP32_SIMT && cfg->fuse_mask >= 0 && (cfg->fuse_mask & BD_FUSE_L12) != 0;
+    e->l12_v2 = e->precision != BD_PRECISION_FP32_SIMT && cfg->fuse_mask >= 0 && (cfg->fuse_mask & BD_FUSE_L12V2) != 0;
+    e->fuse_l12 = e->precision != BD_PRECISION_FP32_SIMT && cfg->fuse_mask >= 0 &&
+                  (cfg->fuse_mask & (BD_FUSE_L12 | BD_FUSE_L12V2)) != 0;
     for (int L = 0; L < BD_N_LAYERS; ++L) {
         LayerDev& l = e->layers[L];
         l.d = w->layers[L];
@@ -495,6 +510,8 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
         l.w_out = l.d.w_in / l.d.stride;
         l.late = L >= first_late;
         l.fused = L >= 1 && ((fuse_mask >> (L - 1)) & 1) && (l.d.w_in / l.d.stride) % 4 == 0 && l.d.cin % 4 == 0;
+        l.fused_v3 = l.fused && use_v3 && l.d.cout % 128 == 0 &&
+                     sep_fused3_supported(l.d.cin, l.d.cout, l.d.h_in, l.d.w_in, l.d.stride);
         auto ptr = [&](int64_t o) -> const float* { return o >= 0 ? e->d_folded + o : nullptr; };
         l.dw_w = ptr(l.d.dw_w); l.dw_b = ptr(l.d.dw_b); l.w = ptr(l.d.w); l.b = ptr(l.d.b);
         const size_t out_px = static_cast<size_t>(l.h_out) * l.w_out;

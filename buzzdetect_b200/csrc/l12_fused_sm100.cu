@@ -1,0 +1,367 @@
+// Layers 1 + 2 in one warp-specialised kernel (sm_100a), version 2:
+//     log-mel patch -> conv 3x3/2 (1->32) -> depthwise 3x3 (32) -> pointwise 32->64      (all with folded BN + ReLU)
+// Reference ops: _conv + the first _separable_conv, embedders/yamnet/yamnet.py:36-74, layer table :77-80.
+//
+// l12_fused_kernel (pw_gemm_sm100.cu) runs its five phases back to back behind CTA-wide barriers and is latency
+// bound.  Here each phase has its own warps and the phases of consecutive tiles overlap through mbarrier rings:
+//
+//   warps 8-11   conv1:   13 log-mel rows per tile, fetched one tile ahead with cp.async (double buffer) -> layer-1
+//                         tile 6 x 34 x 32 fp32 with a one-pixel halo (zero outside the image = the depthwise SAME
+//                         pad) in a 3-deep shared-memory ring
+//   warps 12-15  stencil: depthwise 3x3 from the ring -> hi/lo fp16 straight into the SWIZZLE_128B A tile (2 stages)
+//   warp 1       tcgen05.mma issuer: K = 32 -> two k-steps x 3 products (fp16x3) against the resident weight tile
+//   warps 4-7    epilogue: tcgen05.ld -> scale + bias + ReLU -> smem transpose -> coalesced float4 stores
+//   warp 0       loads the 64 x 32 weight tile once (TMA); warp 2 owns TMEM (2 accumulator stages x 64 columns)
+//
+// A tile = 4 image rows x 32 columns of one patch (128 output pixels); per tile the kernel reads 13 log-mel rows
+// (3.3 KB) and writes 32 KB of layer-2 output: the layer-1 activation (196 KB/patch) and the depthwise planes
+// (2 x 98 KB/patch) never leave the SM.  Tap weights of both stencils live in registers for the whole kernel.
+#include "bd_common.cuh"
+#include "bd_kernels.cuh"
+
+namespace bd {
+
+namespace {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kThreads = 512;
+constexpr int kRows = 4;                                   // image rows per tile
+constexpr int kTileH = kRows + 2, kTileW = 34;
+constexpr int kC1Bytes = kTileH * kTileW * 32 * 4;         // 26,112
+constexpr int kC1Slots = 3;
+constexpr int kAStages = 2;
+constexpr int kATile = kBM * kBK * 2;                      // one fp16 plane, 16 KB (columns 32..63 unused)
+constexpr int kBTile = 64 * kBK * 2;                       // 8 KB per plane
+constexpr int kEpiStride = 36;
+constexpr int kEpiBytes = 4 * 32 * kEpiStride * 4;
+constexpr int kConvWarps = 4, kDwWarps = 4;
+constexpr int kLmRows = 2 * kTileH + 1;                    // 13 log-mel rows feed one layer-1 tile
+constexpr int kLmBytes = kLmRows * kMel * 4;               // 3,328
+
+template <int NSPLIT>
+struct L12Cfg {
+    static constexpr int kPlanes = NSPLIT == 1 ? 1 : 2;
+    static constexpr int kAStageBytes = kPlanes * kATile;
+    static constexpr int kSmemBytes = 1024 + kAStages * kAStageBytes + kPlanes * kBTile + kC1Slots * kC1Bytes + kEpiBytes + 2 * kLmBytes + 256;
+};
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(kThreads, 1)
+l12_fused2_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                  const float* __restrict__ logmel, int hop_frames, int P, const float* __restrict__ w1,
+                  const float* __restrict__ b1, const float* __restrict__ dw_w, const float* __restrict__ dw_b,
+                  const float* __restrict__ bias, float* __restrict__ C, float out_scale) {
+    using Cfg = L12Cfg<NSPLIT>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* a_base = smem;                                            // [2][planes][16 KB]
+    unsigned char* b_base = a_base + kAStages * Cfg::kAStageBytes;           // [planes][8 KB]
+    unsigned char* c1_base = b_base + Cfg::kPlanes * kBTile;                 // [3][26,112]
+    unsigned char* epi_base = c1_base + kC1Slots * kC1Bytes;
+    unsigned char* lm_base = epi_base + kEpiBytes;                           // [2][13][64] fp32 (cp.async double buffer)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lm_base + 2 * kLmBytes);
+    uint64_t* a_full = bars;            // [2]
+    uint64_t* a_empty = bars + 2;       // [2]
+    uint64_t* c1_full = bars + 4;       // [3]
+    uint64_t* c1_empty = bars + 7;      // [3]
+    uint64_t* tmem_full = bars + 10;    // [2]
+    uint64_t* tmem_empty = bars + 12;   // [2]
+    uint64_t* b_bar = bars + 14;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr unsigned tiles_per_patch = 48 / kRows;
+    const unsigned num_tiles = static_cast<unsigned>(P) * tiles_per_patch;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_b_hi);
+        if (NSPLIT > 1) tma_prefetch_desc(&map_b_lo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kAStages; ++i) {
+            mbar_init(&a_full[i], kDwWarps);
+            mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < kC1Slots; ++i) {
+            mbar_init(&c1_full[i], kConvWarps);
+            mbar_init(&c1_empty[i], kDwWarps);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 128);
+        }
+        mbar_init(b_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<128>(tmem_slot);
+    {
+        // columns 32..63 of every A row are never written by the stencil and never read by the MMAs (k-steps 0, 1
+        // only), but clear the tiles once anyway so no uninitialised bit pattern sits in an operand buffer
+        uint4* a = reinterpret_cast<uint4*>(a_base);
+        for (int i = threadIdx.x; i < kAStages * Cfg::kAStageBytes / 16; i += kThreads) a[i] = make_uint4(0, 0, 0, 0);
+        fence_proxy_async_smem();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================================================= weights: once per CTA
+        if (lane == 0) {
+            mbar_arrive_expect_tx(b_bar, Cfg::kPlanes * kBTile);
+            tma_load_2d(b_base, &map_b_hi, b_bar, 0, 0);
+            if (NSPLIT > 1) tma_load_2d(b_base + kBTile, &map_b_lo, b_bar, 0, 0);
+        }
+    } else if (warp == 1) {
+        // ================================================================= MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(kBM, 64);
+            mbar_wait(b_bar, 0);
+            tc_fence_after();
+            const uint32_t bh = smem_u32(b_base), bl = bh + kBTile;
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (unsigned t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                mbar_wait(&a_full[stage], phase);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 64);
+                const uint32_t ah = smem_u32(a_base + stage * Cfg::kAStageBytes), al = ah + kATile;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {                                // K = 32: two k-steps of 16
+                    const uint32_t koff = static_cast<uint32_t>(k) * 32u;
+                    umma_f16_ss(d_tmem, umma_desc_k128(ah + koff), umma_desc_k128(bh + koff), idesc, k != 0 ? 1u : 0u);
+                    if (NSPLIT > 1) {
+                        umma_f16_ss(d_tmem, umma_desc_k128(al + koff), umma_desc_k128(bh + koff), idesc, 1u);
+                        umma_f16_ss(d_tmem, umma_desc_k128(ah + koff), umma_desc_k128(bl + koff), idesc, 1u);
+                    }
+                }
+                umma_commit(&a_empty[stage]);
+                umma_commit(&tmem_full[acc]);
+                if (++stage == kAStages) { stage = 0; phase ^= 1; }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 12) {
+        // ================================================================= depthwise stencil: c1 ring -> A tile
+        const int t = threadIdx.x - 384;                 // 0..127
+        const int quad = t & 7;
+        float4 kk[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) kk[i] = __ldg(reinterpret_cast<const float4*>(dw_w + i * 32 + quad * 4));
+        const float4 bdw = __ldg(reinterpret_cast<const float4*>(dw_b + quad * 4));
+        const uint32_t c1_u32 = smem_u32(c1_base) + static_cast<uint32_t>(quad * 16);
+        const uint32_t a_u32 = smem_u32(a_base);
+        const uint32_t chunk = static_cast<uint32_t>(quad >> 1);
+        int stage = 0, slot = 0;
+        uint32_t phase = 0, sphase = 0;
+        for (unsigned tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait_sleepy(&a_empty[stage], phase ^ 1);
+            mbar_wait_sleepy(&c1_full[slot], sphase);
+            const uint32_t src = c1_u32 + static_cast<uint32_t>(slot * kC1Bytes);
+            const uint32_t a_hi = a_u32 + static_cast<uint32_t>(stage * Cfg::kAStageBytes), a_lo = a_hi + kATile;
+#pragma unroll 1
+            for (int it = 0; it < 2; ++it) {
+                const int strip = (t >> 3) + 16 * it;    // 32 strips of 4 pixels: row = strip / 8, column strip % 8 * 4
+                const int orow = strip >> 3, ws = strip & 7;
+                float4 acc[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[r] = bdw;
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+                    const uint32_t rowp = src + static_cast<uint32_t>((((orow + kh) * kTileW + ws * 4) * 32) * 4);
+                    float4 v[6];
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) v[j] = lds128(rowp + j * 128);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw) {
+                            const float4 x = v[r + kw];
+                            const float4 w4 = kk[kh * 3 + kw];
+                            acc[r].x = fmaf(x.x, w4.x, acc[r].x);
+                            acc[r].y = fmaf(x.y, w4.y, acc[r].y);
+                            acc[r].z = fmaf(x.z, w4.z, acc[r].z);
+                            acc[r].w = fmaf(x.w, w4.w, acc[r].w);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    float4 a = acc[r];
+                    a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+                    const uint32_t row = static_cast<uint32_t>(orow * 32 + ws * 4 + r);
+                    const uint32_t off = (row >> 3) * 1024u + (row & 7u) * 128u + ((chunk ^ (row & 7u)) << 4) +
+                                         (static_cast<uint32_t>(quad & 1) << 3);
+                    const __half h0 = __float2half_rn(a.x), h1 = __float2half_rn(a.y);
+                    const __half h2 = __float2half_rn(a.z), h3 = __float2half_rn(a.w);
+                    __half2 hp[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
+                    sts64(a_hi + off, reinterpret_cast<uint32_t*>(hp)[0], reinterpret_cast<uint32_t*>(hp)[1]);
+                    if (NSPLIT > 1) {
+                        __half2 lp[2] = {__halves2half2(__float2half_rn(a.x - __half2float(h0)),
+                                                        __float2half_rn(a.y - __half2float(h1))),
+                                         __halves2half2(__float2half_rn(a.z - __half2float(h2)),
+                                                        __float2half_rn(a.w - __half2float(h3)))};
+                        sts64(a_lo + off, reinterpret_cast<uint32_t*>(lp)[0], reinterpret_cast<uint32_t*>(lp)[1]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&c1_empty[slot]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[stage]);
+            if (++stage == kAStages) { stage = 0; phase ^= 1; }
+            if (++slot == kC1Slots) { slot = 0; sphase ^= 1; }
+        }
+    } else if (warp >= 8) {
+        // ================================================================= conv1: log-mel -> layer-1 tile (with halo)
+        const int t = threadIdx.x - 256;                 // 0..127
+        const int cg = t & 7;
+        float4 w1r[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) w1r[i] = __ldg(reinterpret_cast<const float4*>(w1 + i * 32 + cg * 4));
+        const float4 b1r = __ldg(reinterpret_cast<const float4*>(b1 + cg * 4));
+        const uint32_t c1_u32 = smem_u32(c1_base) + static_cast<uint32_t>(cg * 16);
+        const uint32_t lm_u32 = smem_u32(lm_base);
+        // log-mel rows of a tile: 13 x 64 floats = 208 16-byte chunks, fetched with cp.async one tile ahead (rows outside
+        // the patch are zero-filled: conv1's SAME pad below row 95, the halo above row 0)
+        auto prefetch = [&](unsigned tile, int buf) {
+            const long long p = tile / tiles_per_patch;
+            const int r0 = static_cast<int>(tile - static_cast<unsigned>(p) * tiles_per_patch) * kRows;
+            const float* in = logmel + p * hop_frames * kMel;
+            const int lm_row0 = 2 * (r0 - 1);
+#pragma unroll
+            for (int c = t; c < kLmRows * 16; c += 128) {
+                const int rr = c >> 4, c4 = c & 15;
+                const int gr = lm_row0 + rr;
+                const bool ok = gr >= 0 && gr < kPatchFrames;
+                const float* src = in + (ok ? gr : 0) * kMel + c4 * 4;
+                const uint32_t dst = lm_u32 + static_cast<uint32_t>(buf * kLmBytes + c * 16);
+                const uint32_t nbytes = ok ? 16u : 0u;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        int slot = 0, buf = 0;
+        uint32_t sphase = 0;
+        if (blockIdx.x < num_tiles) prefetch(blockIdx.x, 0);
+        for (unsigned tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const long long p = tile / tiles_per_patch;
+            const int r0 = static_cast<int>(tile - static_cast<unsigned>(p) * tiles_per_patch) * kRows;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");          // tile's rows visible to all conv warps; previous tile consumed
+            if (tile + gridDim.x < num_tiles) prefetch(tile + gridDim.x, buf ^ 1);
+            mbar_wait_sleepy(&c1_empty[slot], sphase ^ 1);
+            const uint32_t dst = c1_u32 + static_cast<uint32_t>(slot * kC1Bytes);
+            const uint32_t lm = lm_u32 + static_cast<uint32_t>(buf * kLmBytes);
+            int tr = 0, tc = t >> 3;                     // tile pixel (tr, tc); 16 pixels per pass
+#pragma unroll 1
+            for (int px = t >> 3; px < kTileH * kTileW; px += 16) {
+                const int ir = r0 - 1 + tr, ic = tc - 1;
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ir >= 0 && ir < 48 && ic >= 0 && ic < 32) {
+                    a = b1r;
+                    const uint32_t l0 = lm + static_cast<uint32_t>(((2 * tr) * kMel + 2 * ic) * 4);   // staged row 2*tr <-> log-mel row 2*ir
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh) {
+                        float v0, v1, v2;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v0) : "r"(l0 + kh * kMel * 4));
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v1) : "r"(l0 + kh * kMel * 4 + 4));
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v2) : "r"(l0 + kh * kMel * 4 + 8));
+                        if (2 * ic + 2 >= kMel) v2 = 0.f;                         // column 64 is conv1's SAME pad
+                        const float4 wa = w1r[kh * 3 + 0], wb = w1r[kh * 3 + 1], wc = w1r[kh * 3 + 2];
+                        a.x = fmaf(v0, wa.x, a.x); a.y = fmaf(v0, wa.y, a.y); a.z = fmaf(v0, wa.z, a.z); a.w = fmaf(v0, wa.w, a.w);
+                        a.x = fmaf(v1, wb.x, a.x); a.y = fmaf(v1, wb.y, a.y); a.z = fmaf(v1, wb.z, a.z); a.w = fmaf(v1, wb.w, a.w);
+                        a.x = fmaf(v2, wc.x, a.x); a.y = fmaf(v2, wc.y, a.y); a.z = fmaf(v2, wc.z, a.z); a.w = fmaf(v2, wc.w, a.w);
+                    }
+                    a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+                }
+                sts128(dst + static_cast<uint32_t>(px * 128), a);
+                tc += 16;
+                if (tc >= kTileW) { tc -= kTileW; ++tr; }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&c1_full[slot]);
+            if (++slot == kC1Slots) { slot = 0; sphase ^= 1; }
+            buf ^= 1;
+        }
+    } else if (warp >= 4) {
+        // ================================================================= epilogue
+        const int q = warp & 3;
+        const uint32_t stg = smem_u32(epi_base) + static_cast<uint32_t>(q * 32 * kEpiStride * 4);
+        const int srow = lane >> 3, scol = (lane & 7) * 4;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (unsigned tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait_sleepy(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const long long row0 = static_cast<long long>(tile) * kBM + q * 32;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * 64);
+#pragma unroll 1
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
+                    float4 o;
+                    o.x = fmaxf(fmaf(__uint_as_float(r[j + 0]), out_scale, bv.x), 0.f);
+                    o.y = fmaxf(fmaf(__uint_as_float(r[j + 1]), out_scale, bv.y), 0.f);
+                    o.z = fmaxf(fmaf(__uint_as_float(r[j + 2]), out_scale, bv.z), 0.f);
+                    o.w = fmaxf(fmaf(__uint_as_float(r[j + 3]), out_scale, bv.w), 0.f);
+                    sts128(stg + static_cast<uint32_t>((lane * kEpiStride + j) * 4), o);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rl = i * 4 + srow;
+                    const float4 o = lds128(stg + static_cast<uint32_t>((rl * kEpiStride + scol) * 4));
+                    *reinterpret_cast<float4*>(C + (row0 + rl) * 64 + c0 + scol) = o;
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<128>(tmem_base);
+    }
+}
+
+}  // namespace
+
+cudaError_t l12_fused2_init_device() {
+    cudaError_t e = cudaFuncSetAttribute(l12_fused2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L12Cfg<1>::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(l12_fused2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L12Cfg<3>::kSmemBytes);
+}
+
+cudaError_t launch_l12_fused2(const PwGemmPlan& p, const float* logmel, int hop_frames, int P, const float* w1,
+                              const float* b1, const float* dw_w, const float* dw_b, const float* bias, float* C,
+                              int num_sms, cudaStream_t stream) {
+    if (P <= 0) return cudaSuccess;
+    if (p.N != 64 || p.K != 32 || p.block_n != 64) return cudaErrorInvalidValue;
+    const long long tiles = static_cast<long long>(P) * (48 / kRows);
+    if (tiles >= (1LL << 31)) return cudaErrorInvalidValue;
+    const int grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
+    if (p.nsplit == 1)
+        l12_fused2_kernel<1><<<grid, kThreads, L12Cfg<1>::kSmemBytes, stream>>>(p.b_hi, p.b_lo, logmel, hop_frames, P, w1, b1,
+                                                                                dw_w, dw_b, bias, C, p.out_scale);
+    else
+        l12_fused2_kernel<3><<<grid, kThreads, L12Cfg<3>::kSmemBytes, stream>>>(p.b_hi, p.b_lo, logmel, hop_frames, P, w1, b1,
+                                                                                dw_w, dw_b, bias, C, p.out_scale);
+    return cudaGetLastError();
+}
+
+}  // namespace bd

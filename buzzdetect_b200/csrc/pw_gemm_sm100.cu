@@ -696,22 +696,8 @@ l12_fused_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_cons
 
 // ------------------------------------------------------------------------------------------ host side
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (fn == nullptr) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess) {
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-        }
-    }
-    return fn;
-}
+typedef TensorMapEncodeFn EncodeTiledFn;
+EncodeTiledFn get_encode_fn() { return tensor_map_encode_fn(); }
 
 bool encode_2d_f16(CUtensorMap* map, const void* ptr, int rows, int cols, int box_rows) {
     EncodeTiledFn fn = get_encode_fn();
@@ -759,6 +745,19 @@ cudaError_t launch_fused_t(const PwGemmPlan& p, const float* X, const float* dw_
 }
 
 }  // namespace
+
+TensorMapEncodeFn tensor_map_encode_fn() {
+    static TensorMapEncodeFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess) {
+            fn = reinterpret_cast<TensorMapEncodeFn>(p);
+        }
+    }
+    return fn;
+}
 
 float split_weights_f16(const float* w, size_t n, __half* hi, __half* lo) {
     float mx = 0.f;

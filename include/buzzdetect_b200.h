@@ -39,6 +39,8 @@ extern "C" {
 #define BD_PRECISION_FP16X1 1      /* tcgen05, fp16 operands, fp32 accumulate: 1 MMA  (~5e-4 relative)   */
 #define BD_FUSE_CONV1_DW2 (1 << 16)   /* fuse_mask bit: layer 1 + layer-2 depthwise in one kernel              */
 #define BD_FUSE_L12 (1 << 17)         /* fuse_mask bit: layers 1 and 2 entirely in one kernel (tensor-core modes) */
+#define BD_FUSE_V3 (1 << 18)          /* fuse_mask bit: fused layers use sep_fused3_kernel (TMA-staged stencil input) where it applies */
+#define BD_FUSE_L12V2 (1 << 19)       /* fuse_mask bit: layers 1+2 in one warp-specialised kernel (l12_fused2_kernel) */
 #define BD_PRECISION_FP16X3 3      /* tcgen05, hi/lo fp16 split, 3 MMAs: float32-equivalent (default)    */
 
 typedef struct bd_engine bd_engine;

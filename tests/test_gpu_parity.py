@@ -88,7 +88,8 @@ def test_pw_gemm_matches_float64(engines, precision, M, N, K):
 # ------------------------------------------------------------------------------------------------ layer by layer
 @pytest.mark.parametrize("precision,fuse_mask", [("fp32", 0), ("fp16x3", 0), ("fp16", 0), ("fp16x3", 0x7FF),
                                                  ("fp16", 0x7FF), ("fp16x3", 0x10002), ("fp32", 0x10000),
-                                                 ("fp16x3", 0x20002), ("fp16", 0x20000)])
+                                                 ("fp16x3", 0x20002), ("fp16", 0x20000), ("fp16x3", 0x507FF),
+                                                 ("fp16", 0x4003E), ("fp16x3", 0xC0006), ("fp16", 0x80000)])
 def test_every_stage_matches_oracle(engines, yamnet_variables, mel, precision, fuse_mask):
     """fuse_mask 0: separate depthwise / pointwise kernels (every intermediate is observable);
     0x7FF: layers 2..12 run as ONE fused kernel each (depthwise outputs stay in shared memory)."""
@@ -100,7 +101,7 @@ def test_every_stage_matches_oracle(engines, yamnet_variables, mel, precision, f
     for stage in range(0, 28):
         fused_sep = stage >= 2 and stage % 2 == 0 and (fuse_mask >> (stage // 2 - 1)) & 1 and precision != "fp32"
         fused_c1 = stage == 1 and (fuse_mask & 0x10000) and not ((fuse_mask & 1) and precision != "fp32")
-        fused_l12 = stage in (1, 2) and (fuse_mask & 0x20000) and precision != "fp32"
+        fused_l12 = stage in (1, 2) and (fuse_mask & 0xA0000) and precision != "fp32"
         if fused_sep or fused_c1 or fused_l12:
             with pytest.raises(RuntimeError, match="fused away"):
                 e.debug_stage(x, stage)
@@ -130,7 +131,8 @@ def _median_threshold(a):
 @pytest.mark.parametrize("precision,hop,seconds,fuse_mask", [
     ("fp16x3", 96, 61.3, -1), ("fp16x3", 48, 61.3, -1), ("fp32", 96, 20.0, -1), ("fp16x3", 96, 0.5, -1),
     ("fp16x3", 96, 199.68, -1), ("fp16", 96, 61.3, -1), ("fp16x3", 96, 61.3, 0), ("fp16x3", 48, 33.1, 0x7FF),
-    ("fp16x3", 48, 33.1, 0x10002), ("fp16", 96, 20.0, 0x20000),
+    ("fp16x3", 48, 33.1, 0x10002), ("fp16", 96, 20.0, 0x20000), ("fp16x3", 96, 61.3, 0x5003E),
+    ("fp16x3", 48, 33.1, 0x507FF), ("fp16x3", 96, 61.3, 0xC0006), ("fp16x3", 48, 33.1, 0xC0006),
 ])
 def test_predict_matches_oracle(engines, yamnet_variables, mel, head, precision, hop, seconds, fuse_mask):
     e = engines(precision, early_patches=16, late_patches=48, fuse_mask=fuse_mask)   # several early / late sub-batches
