@@ -104,6 +104,34 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* map, uin
         : "memory");
 }
 
+// 256-bit global store (sm_100: STG.256): one full 32-byte sector per lane
+__device__ __forceinline__ void stg256(float* p, float a, float b, float c, float d, float e, float f, float g, float h) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d),
+                 "f"(e), "f"(f), "f"(g), "f"(h)
+                 : "memory");
+}
+
+// 2-D tiled store shared -> global (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const void* map, uint32_t smem_src, int32_t c_inner, int32_t c_outer) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_src), "r"(c_inner), "r"(c_outer)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {      // <= N groups may still be reading their smem source
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Epilogue staging for a TMA store of a [32 rows x 32 float] block with CU_TENSOR_MAP_SWIZZLE_128B: thread = row,
+// 16-byte chunk j of the row lives at chunk (j ^ (row & 7)) -- the 8 lanes of an STS.128 phase hit 8 different
+// chunks, so the transposing write is bank-conflict free.  `stg` must be 1024-byte aligned.
+__device__ __forceinline__ uint32_t epi_swz_addr(uint32_t stg, int row, int j) {
+    return stg + static_cast<uint32_t>(row * 128 + ((j ^ (row & 7)) << 4));
+}
+
 // ------------------------------------------------------------------------------------------ tcgen05
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

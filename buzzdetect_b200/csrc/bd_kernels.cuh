@@ -94,6 +94,8 @@ typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint3
                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 TensorMapEncodeFn tensor_map_encode_fn();
+// Store map for a row-major float32 [rows, cols] output written in [32 x 32] SWIZZLE_128B blocks (epi_swz_addr).
+bool encode_store_map_f32(CUtensorMap* map, float* ptr, long long rows, int cols);
 
 // ---- sep_fused_sm100.cu  (fused separable block v3: TMA-staged depthwise input, see the file header)
 cudaError_t sep_fused3_init_device();
@@ -105,8 +107,9 @@ cudaError_t launch_sep_fused3(const PwGemmPlan& plan, const float* X, const floa
 
 // ---- l12_fused_sm100.cu  (layers 1 + 2, warp-specialised: conv1 warps -> stencil warps -> tcgen05 -> epilogue)
 cudaError_t l12_fused2_init_device();
+// bias_host: the 64 pointwise biases in HOST memory (they travel as a kernel parameter = constant bank).
 cudaError_t launch_l12_fused2(const PwGemmPlan& plan, const float* logmel, int hop_frames, int P, const float* w1,
-                              const float* b1, const float* dw_w, const float* dw_b, const float* bias, float* C,
+                              const float* b1, const float* dw_w, const float* dw_b, const float* bias_host, float* C,
                               int num_sms, cudaStream_t stream);
 
 // ---- resample.cu

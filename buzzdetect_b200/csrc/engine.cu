@@ -67,6 +67,7 @@ struct bd_engine {
     bool use_graph = true;
     cudaStream_t s_compute = nullptr, s_in = nullptr, s_out = nullptr;
     float* d_folded = nullptr;
+    std::vector<float> h_folded;          // host copy: biases travel to the fused kernels as kernel parameters
     FrontendTables* d_tab = nullptr;
     float* d_headW = nullptr;
     float* d_headB = nullptr;
@@ -226,8 +227,8 @@ int enqueue_chunk(bd_engine* e, const float* x, int64_t n, int hop_frames, float
                 // layers 1 + 2 (conv1 -> depthwise -> pointwise) in one kernel: log-mel in, layer-2 output out
                 const LayerDev& l2 = e->layers[1];
                 if (e->l12_v2)
-                    BD_CHECK(e, launch_l12_fused2(l2.plan, lm0, hop_frames, ns, l1.w, l1.b, l2.dw_w, l2.dw_b, l2.b, cur,
-                                                  e->num_sms, st));
+                    BD_CHECK(e, launch_l12_fused2(l2.plan, lm0, hop_frames, ns, l1.w, l1.b, l2.dw_w, l2.dw_b,
+                                                  e->h_folded.data() + l2.d.b, cur, e->num_sms, st));
                 else
                     BD_CHECK(e, launch_l12_fused(l2.plan, lm0, hop_frames, ns, l1.w, l1.b, l2.dw_w, l2.dw_b, l2.b, cur,
                                                  e->num_sms, st));
@@ -460,6 +461,7 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
     if (e->precision != BD_PRECISION_FP32_SIMT) BD_CREATE(l12_fused2_init_device());
 
     // ---- weights
+    e->h_folded.assign(w->folded, w->folded + w->folded_len);
     BD_CREATE(cudaMalloc(&e->d_folded, w->folded_len * sizeof(float)));
     BD_CREATE(cudaMemcpy(e->d_folded, w->folded, w->folded_len * sizeof(float), cudaMemcpyHostToDevice));
     BD_CREATE(cudaMalloc(&e->d_headW, sizeof(float) * kEmb * w->n_classes));

@@ -5,12 +5,12 @@
 // l12_fused_kernel (pw_gemm_sm100.cu) runs its five phases back to back behind CTA-wide barriers and is latency
 // bound.  Here each phase has its own warps and the phases of consecutive tiles overlap through mbarrier rings:
 //
-//   warps 8-11   conv1:   13 log-mel rows per tile, fetched one tile ahead with cp.async (double buffer) -> layer-1
+//   warps 8-11   conv1:   13 log-mel rows per tile, fetched three tiles ahead with cp.async (4-buffer ring) -> layer-1
 //                         tile 6 x 34 x 32 fp32 with a one-pixel halo (zero outside the image = the depthwise SAME
 //                         pad) in a 3-deep shared-memory ring
 //   warps 12-15  stencil: depthwise 3x3 from the ring -> hi/lo fp16 straight into the SWIZZLE_128B A tile (2 stages)
 //   warp 1       tcgen05.mma issuer: K = 32 -> two k-steps x 3 products (fp16x3) against the resident weight tile
-//   warps 4-7    epilogue: tcgen05.ld -> scale + bias + ReLU -> smem transpose -> coalesced float4 stores
+//   warps 4-7    epilogue: tcgen05.ld -> scale + bias (constant bank) + ReLU -> swizzled smem block -> TMA store
 //   warp 0       loads the 64 x 32 weight tile once (TMA); warp 2 owns TMEM (2 accumulator stages x 64 columns)
 //
 // A tile = 4 image rows x 32 columns of one patch (128 output pixels); per tile the kernel reads 13 log-mel rows
@@ -33,42 +33,48 @@ constexpr int kC1Slots = 3;
 constexpr int kAStages = 2;
 constexpr int kATile = kBM * kBK * 2;                      // one fp16 plane, 16 KB (columns 32..63 unused)
 constexpr int kBTile = 64 * kBK * 2;                       // 8 KB per plane
-constexpr int kEpiStride = 36;
-constexpr int kEpiBytes = 4 * 32 * kEpiStride * 4;
+constexpr int kEpiBufBytes = 32 * 128;                     // one [32 rows x 32 float] swizzled block
+constexpr int kEpiBytes = 4 * 2 * kEpiBufBytes;            // 4 epilogue warps x 2 buffers
 constexpr int kConvWarps = 4, kDwWarps = 4;
+
+struct Bias64 { float v[64]; };                            // kernel parameter = constant bank: uniform reads cost no L1 traffic
 constexpr int kLmRows = 2 * kTileH + 1;                    // 13 log-mel rows feed one layer-1 tile
 constexpr int kLmBytes = kLmRows * kMel * 4;               // 3,328
+constexpr int kLmBufs = 4;                                 // cp.async ring: rows are fetched 3 tiles ahead (DRAM latency > tile time)
 
 template <int NSPLIT>
 struct L12Cfg {
     static constexpr int kPlanes = NSPLIT == 1 ? 1 : 2;
     static constexpr int kAStageBytes = kPlanes * kATile;
-    static constexpr int kSmemBytes = 1024 + kAStages * kAStageBytes + kPlanes * kBTile + kC1Slots * kC1Bytes + kEpiBytes + 2 * kLmBytes + 256;
+    static constexpr int kSmemBytes = 1024 + kAStages * kAStageBytes + kEpiBytes + kPlanes * kBTile + kC1Slots * kC1Bytes + kLmBufs * kLmBytes + 256;
 };
+
+static_assert(L12Cfg<3>::kSmemBytes <= 227 * 1024, "layers-1+2 kernel: shared memory budget");
 
 template <int NSPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 l12_fused2_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                  const __grid_constant__ CUtensorMap map_c, const __grid_constant__ Bias64 biasp,
                   const float* __restrict__ logmel, int hop_frames, int P, const float* __restrict__ w1,
                   const float* __restrict__ b1, const float* __restrict__ dw_w, const float* __restrict__ dw_b,
-                  const float* __restrict__ bias, float* __restrict__ C, float out_scale) {
+                  float out_scale) {
     using Cfg = L12Cfg<NSPLIT>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* a_base = smem;                                            // [2][planes][16 KB]
-    unsigned char* b_base = a_base + kAStages * Cfg::kAStageBytes;           // [planes][8 KB]
+    unsigned char* epi_base = a_base + kAStages * Cfg::kAStageBytes;         // [4 warps][2][4 KB], 1024-byte aligned
+    unsigned char* b_base = epi_base + kEpiBytes;                            // [planes][8 KB]
     unsigned char* c1_base = b_base + Cfg::kPlanes * kBTile;                 // [3][26,112]
-    unsigned char* epi_base = c1_base + kC1Slots * kC1Bytes;
-    unsigned char* lm_base = epi_base + kEpiBytes;                           // [2][13][64] fp32 (cp.async double buffer)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(lm_base + 2 * kLmBytes);
+    unsigned char* lm_base = c1_base + kC1Slots * kC1Bytes;                  // [4][13][64] fp32 (cp.async ring)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lm_base + kLmBufs * kLmBytes);
     uint64_t* a_full = bars;            // [2]
     uint64_t* a_empty = bars + 2;       // [2]
-    uint64_t* c1_full = bars + 4;       // [3]
-    uint64_t* c1_empty = bars + 7;      // [3]
-    uint64_t* tmem_full = bars + 10;    // [2]
-    uint64_t* tmem_empty = bars + 12;   // [2]
-    uint64_t* b_bar = bars + 14;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+    uint64_t* c1_full = bars + 4;       // [kC1Slots <= 4]
+    uint64_t* c1_empty = bars + 8;      // [kC1Slots <= 4]
+    uint64_t* tmem_full = bars + 12;    // [2]
+    uint64_t* tmem_empty = bars + 14;   // [2]
+    uint64_t* b_bar = bars + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr unsigned tiles_per_patch = 48 / kRows;
@@ -77,6 +83,7 @@ l12_fused2_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_con
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_b_hi);
         if (NSPLIT > 1) tma_prefetch_desc(&map_b_lo);
+        tma_prefetch_desc(&map_c);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kAStages; ++i) {
@@ -101,6 +108,10 @@ l12_fused2_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_con
         uint4* a = reinterpret_cast<uint4*>(a_base);
         for (int i = threadIdx.x; i < kAStages * Cfg::kAStageBytes / 16; i += kThreads) a[i] = make_uint4(0, 0, 0, 0);
         fence_proxy_async_smem();
+        // layer-1 ring: tile columns 0 and 33 lie outside the image for every tile (the depthwise SAME pad); they are
+        // zeroed here once and never written again
+        uint4* c = reinterpret_cast<uint4*>(c1_base);
+        for (int i = threadIdx.x; i < kC1Slots * kC1Bytes / 16; i += kThreads) c[i] = make_uint4(0, 0, 0, 0);
     }
     tc_fence_before();
     __syncthreads();
@@ -162,49 +173,59 @@ l12_fused2_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_con
             mbar_wait_sleepy(&c1_full[slot], sphase);
             const uint32_t src = c1_u32 + static_cast<uint32_t>(slot * kC1Bytes);
             const uint32_t a_hi = a_u32 + static_cast<uint32_t>(stage * Cfg::kAStageBytes), a_lo = a_hi + kATile;
-#pragma unroll 1
-            for (int it = 0; it < 2; ++it) {
-                const int strip = (t >> 3) + 16 * it;    // 32 strips of 4 pixels: row = strip / 8, column strip % 8 * 4
-                const int orow = strip >> 3, ws = strip & 7;
-                float4 acc[4];
+            {
+                // block of 4 columns x 2 rows of outputs: 4 input rows x 6 columns, 3 LDS.128 per output vector
+                const int blk = t >> 3;                  // 0..15
+                const int brow = blk >> 3, ws = blk & 7;
+                float4 acc[2][4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) acc[r] = bdw;
+                for (int o = 0; o < 2; ++o)
 #pragma unroll
-                for (int kh = 0; kh < 3; ++kh) {
-                    const uint32_t rowp = src + static_cast<uint32_t>((((orow + kh) * kTileW + ws * 4) * 32) * 4);
+                    for (int r = 0; r < 4; ++r) acc[o][r] = bdw;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t rowp = src + static_cast<uint32_t>((((2 * brow + i) * kTileW + ws * 4) * 32) * 4);
                     float4 v[6];
 #pragma unroll
                     for (int j = 0; j < 6; ++j) v[j] = lds128(rowp + j * 128);
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
+                    for (int o = 0; o < 2; ++o) {
+                        const int kh = i - o;
+                        if (kh < 0 || kh > 2) continue;
 #pragma unroll
-                        for (int kw = 0; kw < 3; ++kw) {
-                            const float4 x = v[r + kw];
-                            const float4 w4 = kk[kh * 3 + kw];
-                            acc[r].x = fmaf(x.x, w4.x, acc[r].x);
-                            acc[r].y = fmaf(x.y, w4.y, acc[r].y);
-                            acc[r].z = fmaf(x.z, w4.z, acc[r].z);
-                            acc[r].w = fmaf(x.w, w4.w, acc[r].w);
+                        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                            for (int kw = 0; kw < 3; ++kw) {
+                                const float4 x = v[r + kw];
+                                const float4 w4 = kk[kh * 3 + kw];
+                                acc[o][r].x = fmaf(x.x, w4.x, acc[o][r].x);
+                                acc[o][r].y = fmaf(x.y, w4.y, acc[o][r].y);
+                                acc[o][r].z = fmaf(x.z, w4.z, acc[o][r].z);
+                                acc[o][r].w = fmaf(x.w, w4.w, acc[o][r].w);
+                            }
                         }
                     }
                 }
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    float4 a = acc[r];
-                    a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
-                    const uint32_t row = static_cast<uint32_t>(orow * 32 + ws * 4 + r);
-                    const uint32_t off = (row >> 3) * 1024u + (row & 7u) * 128u + ((chunk ^ (row & 7u)) << 4) +
-                                         (static_cast<uint32_t>(quad & 1) << 3);
-                    const __half h0 = __float2half_rn(a.x), h1 = __float2half_rn(a.y);
-                    const __half h2 = __float2half_rn(a.z), h3 = __float2half_rn(a.w);
-                    __half2 hp[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
-                    sts64(a_hi + off, reinterpret_cast<uint32_t*>(hp)[0], reinterpret_cast<uint32_t*>(hp)[1]);
-                    if (NSPLIT > 1) {
-                        __half2 lp[2] = {__halves2half2(__float2half_rn(a.x - __half2float(h0)),
-                                                        __float2half_rn(a.y - __half2float(h1))),
-                                         __halves2half2(__float2half_rn(a.z - __half2float(h2)),
-                                                        __float2half_rn(a.w - __half2float(h3)))};
-                        sts64(a_lo + off, reinterpret_cast<uint32_t*>(lp)[0], reinterpret_cast<uint32_t*>(lp)[1]);
+                for (int o = 0; o < 2; ++o) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        float4 a = acc[o][r];
+                        a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+                        const uint32_t row = static_cast<uint32_t>((2 * brow + o) * 32 + ws * 4 + r);
+                        const uint32_t off = (row >> 3) * 1024u + (row & 7u) * 128u + ((chunk ^ (row & 7u)) << 4) +
+                                             (static_cast<uint32_t>(quad & 1) << 3);
+                        const __half h0 = __float2half_rn(a.x), h1 = __float2half_rn(a.y);
+                        const __half h2 = __float2half_rn(a.z), h3 = __float2half_rn(a.w);
+                        __half2 hp[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
+                        sts64(a_hi + off, reinterpret_cast<uint32_t*>(hp)[0], reinterpret_cast<uint32_t*>(hp)[1]);
+                        if (NSPLIT > 1) {
+                            __half2 lp[2] = {__halves2half2(__float2half_rn(a.x - __half2float(h0)),
+                                                            __float2half_rn(a.y - __half2float(h1))),
+                                             __halves2half2(__float2half_rn(a.z - __half2float(h2)),
+                                                            __float2half_rn(a.w - __half2float(h3)))};
+                            sts64(a_lo + off, reinterpret_cast<uint32_t*>(lp)[0], reinterpret_cast<uint32_t*>(lp)[1]);
+                        }
                     }
                 }
             }
@@ -229,6 +250,10 @@ l12_fused2_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_con
         // log-mel rows of a tile: 13 x 64 floats = 208 16-byte chunks, fetched with cp.async one tile ahead (rows outside
         // the patch are zero-filled: conv1's SAME pad below row 95, the halo above row 0)
         auto prefetch = [&](unsigned tile, int buf) {
+            if (tile >= num_tiles) {                         // keep one commit group per tile so wait_group counts line up
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                return;
+            }
             const long long p = tile / tiles_per_patch;
             const int r0 = static_cast<int>(tile - static_cast<unsigned>(p) * tiles_per_patch) * kRows;
             const float* in = logmel + p * hop_frames * kMel;
@@ -247,87 +272,93 @@ l12_fused2_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_con
         };
         int slot = 0, buf = 0;
         uint32_t sphase = 0;
-        if (blockIdx.x < num_tiles) prefetch(blockIdx.x, 0);
+#pragma unroll
+        for (int i = 0; i < kLmBufs - 1; ++i) prefetch(blockIdx.x + i * gridDim.x, i);
         for (unsigned tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const long long p = tile / tiles_per_patch;
             const int r0 = static_cast<int>(tile - static_cast<unsigned>(p) * tiles_per_patch) * kRows;
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("cp.async.wait_group %0;" ::"n"(kLmBufs - 2) : "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");          // tile's rows visible to all conv warps; previous tile consumed
-            if (tile + gridDim.x < num_tiles) prefetch(tile + gridDim.x, buf ^ 1);
+            prefetch(tile + (kLmBufs - 1) * gridDim.x, (buf + kLmBufs - 1) % kLmBufs);
             mbar_wait_sleepy(&c1_empty[slot], sphase ^ 1);
             const uint32_t dst = c1_u32 + static_cast<uint32_t>(slot * kC1Bytes);
             const uint32_t lm = lm_u32 + static_cast<uint32_t>(buf * kLmBytes);
-            int tr = 0, tc = t >> 3;                     // tile pixel (tr, tc); 16 pixels per pass
+            // thread = (channel quad, pair of interior columns): image columns ic0 = 2*pair, ic0 + 1 of tile row tr; the
+            // five log-mel columns 2*ic0 .. 2*ic0+4 of a row come from one LDS.128 + one LDS.32
 #pragma unroll 1
-            for (int px = t >> 3; px < kTileH * kTileW; px += 16) {
-                const int ir = r0 - 1 + tr, ic = tc - 1;
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ir >= 0 && ir < 48 && ic >= 0 && ic < 32) {
-                    a = b1r;
-                    const uint32_t l0 = lm + static_cast<uint32_t>(((2 * tr) * kMel + 2 * ic) * 4);   // staged row 2*tr <-> log-mel row 2*ir
+            for (int item = t >> 3; item < kTileH * 16; item += 16) {
+                const int tr = item >> 4, pair = item & 15;
+                const int ir = r0 - 1 + tr, ic0 = 2 * pair;
+                float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+                if (ir >= 0 && ir < 48) {
+                    a0 = b1r; a1 = b1r;
+                    const uint32_t l0 = lm + static_cast<uint32_t>(((2 * tr) * kMel + 2 * ic0) * 4);   // staged row 2*tr <-> log-mel row 2*ir
 #pragma unroll
                     for (int kh = 0; kh < 3; ++kh) {
-                        float v0, v1, v2;
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v0) : "r"(l0 + kh * kMel * 4));
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v1) : "r"(l0 + kh * kMel * 4 + 4));
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v2) : "r"(l0 + kh * kMel * 4 + 8));
-                        if (2 * ic + 2 >= kMel) v2 = 0.f;                         // column 64 is conv1's SAME pad
+                        const float4 v = lds128(l0 + kh * kMel * 4);
+                        float v4;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v4) : "r"(l0 + kh * kMel * 4 + 16));
+                        if (pair == 15) v4 = 0.f;                                 // column 64 is conv1's SAME pad
                         const float4 wa = w1r[kh * 3 + 0], wb = w1r[kh * 3 + 1], wc = w1r[kh * 3 + 2];
-                        a.x = fmaf(v0, wa.x, a.x); a.y = fmaf(v0, wa.y, a.y); a.z = fmaf(v0, wa.z, a.z); a.w = fmaf(v0, wa.w, a.w);
-                        a.x = fmaf(v1, wb.x, a.x); a.y = fmaf(v1, wb.y, a.y); a.z = fmaf(v1, wb.z, a.z); a.w = fmaf(v1, wb.w, a.w);
-                        a.x = fmaf(v2, wc.x, a.x); a.y = fmaf(v2, wc.y, a.y); a.z = fmaf(v2, wc.z, a.z); a.w = fmaf(v2, wc.w, a.w);
+                        a0.x = fmaf(v.x, wa.x, a0.x); a0.y = fmaf(v.x, wa.y, a0.y); a0.z = fmaf(v.x, wa.z, a0.z); a0.w = fmaf(v.x, wa.w, a0.w);
+                        a0.x = fmaf(v.y, wb.x, a0.x); a0.y = fmaf(v.y, wb.y, a0.y); a0.z = fmaf(v.y, wb.z, a0.z); a0.w = fmaf(v.y, wb.w, a0.w);
+                        a0.x = fmaf(v.z, wc.x, a0.x); a0.y = fmaf(v.z, wc.y, a0.y); a0.z = fmaf(v.z, wc.z, a0.z); a0.w = fmaf(v.z, wc.w, a0.w);
+                        a1.x = fmaf(v.z, wa.x, a1.x); a1.y = fmaf(v.z, wa.y, a1.y); a1.z = fmaf(v.z, wa.z, a1.z); a1.w = fmaf(v.z, wa.w, a1.w);
+                        a1.x = fmaf(v.w, wb.x, a1.x); a1.y = fmaf(v.w, wb.y, a1.y); a1.z = fmaf(v.w, wb.z, a1.z); a1.w = fmaf(v.w, wb.w, a1.w);
+                        a1.x = fmaf(v4, wc.x, a1.x); a1.y = fmaf(v4, wc.y, a1.y); a1.z = fmaf(v4, wc.z, a1.z); a1.w = fmaf(v4, wc.w, a1.w);
                     }
-                    a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+                    a0.x = fmaxf(a0.x, 0.f); a0.y = fmaxf(a0.y, 0.f); a0.z = fmaxf(a0.z, 0.f); a0.w = fmaxf(a0.w, 0.f);
+                    a1.x = fmaxf(a1.x, 0.f); a1.y = fmaxf(a1.y, 0.f); a1.z = fmaxf(a1.z, 0.f); a1.w = fmaxf(a1.w, 0.f);
                 }
-                sts128(dst + static_cast<uint32_t>(px * 128), a);
-                tc += 16;
-                if (tc >= kTileW) { tc -= kTileW; ++tr; }
+                const uint32_t o = dst + static_cast<uint32_t>((tr * kTileW + 1 + ic0) * 128);        // tile column = image column + 1
+                sts128(o, a0);
+                sts128(o + 128, a1);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&c1_full[slot]);
             if (++slot == kC1Slots) { slot = 0; sphase ^= 1; }
-            buf ^= 1;
+            if (++buf == kLmBufs) buf = 0;
         }
     } else if (warp >= 4) {
         // ================================================================= epilogue
         const int q = warp & 3;
-        const uint32_t stg = smem_u32(epi_base) + static_cast<uint32_t>(q * 32 * kEpiStride * 4);
-        const int srow = lane >> 3, scol = (lane & 7) * 4;
+        const uint32_t stg0 = smem_u32(epi_base) + static_cast<uint32_t>(q * 2 * kEpiBufBytes);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (unsigned tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             mbar_wait_sleepy(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            const long long row0 = static_cast<long long>(tile) * kBM + q * 32;
+            const int row0 = static_cast<int>(tile) * kBM + q * 32;      // < 2^31: checked by the launcher
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * 64);
-#pragma unroll 1
-            for (int c0 = 0; c0 < 64; c0 += 32) {
+#pragma unroll
+            for (int cb = 0; cb < 2; ++cb) {
                 uint32_t r[32];
-                tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), r);
+                tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(cb * 32), r);
+                const uint32_t stg = stg0 + static_cast<uint32_t>(cb * kEpiBufBytes);
+                if (lane == 0) tma_store_wait_read<1>();              // the store that last read this buffer is done
+                __syncwarp();
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
+                for (int j = 0; j < 8; ++j) {
                     float4 o;
-                    o.x = fmaxf(fmaf(__uint_as_float(r[j + 0]), out_scale, bv.x), 0.f);
-                    o.y = fmaxf(fmaf(__uint_as_float(r[j + 1]), out_scale, bv.y), 0.f);
-                    o.z = fmaxf(fmaf(__uint_as_float(r[j + 2]), out_scale, bv.z), 0.f);
-                    o.w = fmaxf(fmaf(__uint_as_float(r[j + 3]), out_scale, bv.w), 0.f);
-                    sts128(stg + static_cast<uint32_t>((lane * kEpiStride + j) * 4), o);
+                    o.x = fmaxf(fmaf(__uint_as_float(r[4 * j + 0]), out_scale, biasp.v[cb * 32 + 4 * j + 0]), 0.f);
+                    o.y = fmaxf(fmaf(__uint_as_float(r[4 * j + 1]), out_scale, biasp.v[cb * 32 + 4 * j + 1]), 0.f);
+                    o.z = fmaxf(fmaf(__uint_as_float(r[4 * j + 2]), out_scale, biasp.v[cb * 32 + 4 * j + 2]), 0.f);
+                    o.w = fmaxf(fmaf(__uint_as_float(r[4 * j + 3]), out_scale, biasp.v[cb * 32 + 4 * j + 3]), 0.f);
+                    sts128(epi_swz_addr(stg, lane, j), o);
                 }
+                fence_proxy_async_smem();
                 __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int rl = i * 4 + srow;
-                    const float4 o = lds128(stg + static_cast<uint32_t>((rl * kEpiStride + scol) * 4));
-                    *reinterpret_cast<float4*>(C + (row0 + rl) * 64 + c0 + scol) = o;
+                if (lane == 0) {
+                    tma_store_2d(&map_c, stg, cb * 32, row0);
+                    tma_store_commit();
                 }
-                __syncwarp();
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (lane == 0) tma_store_wait_all();
     }
 
     tc_fence_before();
@@ -348,19 +379,23 @@ cudaError_t l12_fused2_init_device() {
 }
 
 cudaError_t launch_l12_fused2(const PwGemmPlan& p, const float* logmel, int hop_frames, int P, const float* w1,
-                              const float* b1, const float* dw_w, const float* dw_b, const float* bias, float* C,
+                              const float* b1, const float* dw_w, const float* dw_b, const float* bias_host, float* C,
                               int num_sms, cudaStream_t stream) {
     if (P <= 0) return cudaSuccess;
-    if (p.N != 64 || p.K != 32 || p.block_n != 64) return cudaErrorInvalidValue;
+    if (p.N != 64 || p.K != 32 || p.block_n != 64 || bias_host == nullptr) return cudaErrorInvalidValue;
     const long long tiles = static_cast<long long>(P) * (48 / kRows);
-    if (tiles >= (1LL << 31)) return cudaErrorInvalidValue;
+    if (tiles * kBM >= (1LL << 31)) return cudaErrorInvalidValue;
     const int grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
+    CUtensorMap map_c;
+    if (!encode_store_map_f32(&map_c, C, tiles * kBM, 64)) return cudaErrorUnknown;
+    Bias64 bp;
+    for (int i = 0; i < 64; ++i) bp.v[i] = bias_host[i];
     if (p.nsplit == 1)
-        l12_fused2_kernel<1><<<grid, kThreads, L12Cfg<1>::kSmemBytes, stream>>>(p.b_hi, p.b_lo, logmel, hop_frames, P, w1, b1,
-                                                                                dw_w, dw_b, bias, C, p.out_scale);
+        l12_fused2_kernel<1><<<grid, kThreads, L12Cfg<1>::kSmemBytes, stream>>>(p.b_hi, p.b_lo, map_c, bp, logmel, hop_frames, P,
+                                                                                w1, b1, dw_w, dw_b, p.out_scale);
     else
-        l12_fused2_kernel<3><<<grid, kThreads, L12Cfg<3>::kSmemBytes, stream>>>(p.b_hi, p.b_lo, logmel, hop_frames, P, w1, b1,
-                                                                                dw_w, dw_b, bias, C, p.out_scale);
+        l12_fused2_kernel<3><<<grid, kThreads, L12Cfg<3>::kSmemBytes, stream>>>(p.b_hi, p.b_lo, map_c, bp, logmel, hop_frames, P,
+                                                                                w1, b1, dw_w, dw_b, p.out_scale);
     return cudaGetLastError();
 }
 

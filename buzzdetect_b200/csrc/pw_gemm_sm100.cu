@@ -759,6 +759,18 @@ TensorMapEncodeFn tensor_map_encode_fn() {
     return fn;
 }
 
+bool encode_store_map_f32(CUtensorMap* map, float* ptr, long long rows, int cols) {
+    TensorMapEncodeFn fn = tensor_map_encode_fn();
+    if (fn == nullptr || cols % 32 != 0 || rows < 1) return false;
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 float split_weights_f16(const float* w, size_t n, __half* hi, __half* lo) {
     float mx = 0.f;
     for (size_t i = 0; i < n; ++i) mx = fmaxf(mx, fabsf(w[i]));
