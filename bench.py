@@ -258,7 +258,7 @@ def run_ours(args, rank, world, local):
     per_layer = {}
     fam = {"pw_gemm_kernel": {"ms": 0.0, "launches": 0, "flop": 0.0, "bytes": 0.0},
            "pw_gemm_kernel[layers 7-14]": {"ms": 0.0, "launches": 0, "flop": 0.0, "bytes": 0.0},
-           "sep_fused_kernel": {"ms": 0.0, "launches": 0, "flop": 0.0, "bytes": 0.0},
+           "sep_fused3_kernel": {"ms": 0.0, "launches": 0, "flop": 0.0, "bytes": 0.0},
            "depthwise_kernel": {"ms": 0.0, "launches": 0, "flop": 0.0, "bytes": 0.0}}
     for i, (kind, stride, cin, cout, H, W) in enumerate(LAYERS[1:]):
         v = prof["layers"][f"L{i + 2}"]
@@ -275,19 +275,25 @@ def run_ours(args, rank, world, local):
             f = fam["depthwise_kernel"]
             f["ms"] += v["dw_ms"]; f["launches"] += v["dw_launches"]; f["bytes"] += dw_bytes
         if v["pw_launches"]:
-            names = ["sep_fused_kernel"] if fused else (["pw_gemm_kernel"] + (["pw_gemm_kernel[layers 7-14]"] if i + 2 >= 7 else []))
+            names = ["sep_fused3_kernel"] if fused else (["pw_gemm_kernel"] + (["pw_gemm_kernel[layers 7-14]"] if i + 2 >= 7 else []))
             for nm in names:
                 f = fam[nm]
                 f["ms"] += v["pw_ms"]; f["launches"] += v["pw_launches"]; f["flop"] += pw_flop
                 f["bytes"] += ((H * W * cin + ho * wo * cout) * 4.0 * P) if fused else pw_bytes
-    c1_bytes = (96 * 64 + 48 * 32 * 32) * 4.0 * P
-    fam["conv1_dw2_kernel"] = {"ms": prof["conv1"]["ms"], "launches": prof["conv1"]["launches"], "flop": 0.0,
-                               "bytes": c1_bytes}
+    l12 = prof["layers"]["L2"]["pw_launches"] == 0 and prof["layers"]["L2"]["dw_launches"] == 0
+    if l12:     # layers 1+2 in one kernel: log-mel patch in, layer-2 output out
+        fam["l12_fused2_kernel"] = {"ms": prof["conv1"]["ms"], "launches": prof["conv1"]["launches"], "flop": 0.0,
+                                    "bytes": (96 * 64 + 48 * 32 * 64) * 4.0 * P}
+    else:       # layer 1 + layer-2 depthwise: log-mel patch in, hi/lo planes (4 B per element) out
+        fam["conv1_dw2_kernel"] = {"ms": prof["conv1"]["ms"], "launches": prof["conv1"]["launches"], "flop": 0.0,
+                                   "bytes": (96 * 64 + 48 * 32 * 32) * 4.0 * P}
     fam["logmel_kernel"] = {"ms": prof["frontend"]["ms"], "launches": prof["frontend"]["launches"], "flop": 0.0,
                             "bytes": FRONTEND_BYTES_PER_PATCH * float(P)}
     total_prof_ms = sum(prof[k]["ms"] for k in ("frontend", "conv1", "depthwise", "pointwise", "pool_head"))
     traffic_tab = {}
-    tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    tpath = os.path.join(ROOT, "profiles", "traffic_r1b.json")
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic_tab = json.load(f)

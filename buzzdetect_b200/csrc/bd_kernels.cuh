@@ -101,8 +101,9 @@ bool encode_store_map_f32(CUtensorMap* map, float* ptr, long long rows, int cols
 cudaError_t sep_fused3_init_device();
 bool sep_fused3_supported(int K, int N, int H, int W, int stride);
 // X: [P,H,W,K] float32 NHWC (16-byte aligned); C: [P*(H/stride)*(W/stride), N].  Uses the plan's weight maps.
+// bias_host: the N pointwise biases in HOST memory (kernel parameter = constant bank).
 cudaError_t launch_sep_fused3(const PwGemmPlan& plan, const float* X, const float* dw_w, const float* dw_b,
-                              const float* bias, float* C, int P, int H, int W, int stride, int num_sms,
+                              const float* bias_host, float* C, int P, int H, int W, int stride, int num_sms,
                               cudaStream_t stream);
 
 // ---- l12_fused_sm100.cu  (layers 1 + 2, warp-specialised: conv1 warps -> stencil warps -> tcgen05 -> epilogue)

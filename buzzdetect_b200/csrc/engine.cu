@@ -195,7 +195,7 @@ int enqueue_chunk(bd_engine* e, const float* x, int64_t n, int hop_frames, float
     auto fused = [&](int L, const float* in, int np, float* out) -> int {
         const LayerDev& l = e->layers[L];
         if (l.fused_v3)
-            BD_CHECK(e, launch_sep_fused3(l.plan, in, l.dw_w, l.dw_b, l.b, out, np, l.d.h_in, l.d.w_in, l.d.stride,
+            BD_CHECK(e, launch_sep_fused3(l.plan, in, l.dw_w, l.dw_b, e->h_folded.data() + l.d.b, out, np, l.d.h_in, l.d.w_in, l.d.stride,
                                           e->num_sms, st));
         else
             BD_CHECK(e, launch_sep_fused(l.plan, in, l.dw_w, l.dw_b, l.b, out, np, l.d.h_in, l.d.w_in, l.d.stride,
@@ -496,14 +496,15 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
     const int first_late = e->first_late;                        // layer 7 (index 6): its depthwise output feeds the late phase
     // which separable blocks run fused: bit (L-2) for layer L.  Measured on B200 (profiles/fusion_r1.md): with the
     // current register-fed producers only layer 3 (stride 2, K=64) beats the two-kernel path, so that is the default.
-    const int fuse_mask = e->precision == BD_PRECISION_FP32_SIMT ? 0 : (cfg->fuse_mask < 0 ? 0x2 : (cfg->fuse_mask & 0x1FFF));
-    const bool use_v3 = cfg->fuse_mask >= 0 && (cfg->fuse_mask & BD_FUSE_V3) != 0;
-    e->fuse_conv1 = cfg->fuse_mask < 0 || (cfg->fuse_mask & BD_FUSE_CONV1_DW2) != 0;
-    // measured (profiles/fusion_r1.md): the single-kernel layers-1+2 path is latency bound (1.18 ms per audio-hour vs
-    // 0.44 + 0.70 for conv1_dw2 + pointwise), so it is opt-in
-    e->l12_v2 = e->precision != BD_PRECISION_FP32_SIMT && cfg->fuse_mask >= 0 && (cfg->fuse_mask & BD_FUSE_L12V2) != 0;
-    e->fuse_l12 = e->precision != BD_PRECISION_FP32_SIMT && cfg->fuse_mask >= 0 &&
-                  (cfg->fuse_mask & (BD_FUSE_L12 | BD_FUSE_L12V2)) != 0;
+    // Default (fuse_mask < 0), measured on B200 (profiles/r1_summary.md): layers 1+2 in the warp-specialised
+    // l12_fused2_kernel, layers 3..6 in sep_fused3_kernel (TMA-staged stencil input); layer 7 and the 6x4 / 3x2 layers
+    // stay as depthwise + GEMM pairs (their output tiles would straddle patches).
+    const int cfg_mask = cfg->fuse_mask < 0 ? (BD_FUSE_L12V2 | BD_FUSE_V3 | BD_FUSE_CONV1_DW2 | 0x1E) : cfg->fuse_mask;
+    const int fuse_mask = e->precision == BD_PRECISION_FP32_SIMT ? 0 : (cfg_mask & 0x1FFF);
+    const bool use_v3 = (cfg_mask & BD_FUSE_V3) != 0;
+    e->fuse_conv1 = (cfg_mask & BD_FUSE_CONV1_DW2) != 0;
+    e->l12_v2 = e->precision != BD_PRECISION_FP32_SIMT && (cfg_mask & BD_FUSE_L12V2) != 0;
+    e->fuse_l12 = e->precision != BD_PRECISION_FP32_SIMT && (cfg_mask & (BD_FUSE_L12 | BD_FUSE_L12V2)) != 0;
     for (int L = 0; L < BD_N_LAYERS; ++L) {
         LayerDev& l = e->layers[L];
         l.d = w->layers[L];

@@ -15,7 +15,7 @@
 //   warp 1      tcgen05.mma issuer (M=128, N=BN, K=16; 3 MMAs per k-step in the fp16x3 split mode)
 //   warp 2      TMEM allocator
 //   warp 3      input TMA (float32 boxes -> in_ring)
-//   warps 4-7   epilogue: tcgen05.ld -> scale + bias + ReLU -> smem transpose -> coalesced float4 stores
+//   warps 4-7   epilogue: tcgen05.ld -> scale + bias (constant bank) + ReLU -> swizzled smem block -> TMA store
 //   warps 8-15  stencil producers: depthwise from in_ring, hi/lo fp16 straight into the swizzled A tile
 //
 // An output tile is TRt image rows x Wo columns of ONE patch (<= 128 pixels, so tiles never straddle patches and one
@@ -33,8 +33,11 @@ constexpr int kCB = 32;                                          // channels per
 constexpr int kF3Threads = 512;
 constexpr int kF3ProdWarps = 8;
 constexpr int kF3ProdThreads = kF3ProdWarps * 32;
-constexpr int kEpiStride = 36;
-constexpr int kEpiBytes = 4 * 32 * kEpiStride * 4;
+constexpr int kEpiBufBytes = 32 * 128;                           // one [32 rows x 32 float] swizzled block per epilogue warp
+constexpr int kEpiBytes = 4 * kEpiBufBytes;
+constexpr int kMaxN = 512;
+
+struct BiasParam { float v[kMaxN]; };                            // kernel parameter = constant bank (no L1 traffic)
 constexpr int kABStages = 2;
 constexpr int kMaxInStages = 6;
 constexpr int kSmemMax = 227 * 1024;
@@ -52,8 +55,6 @@ struct F3Cfg {
 struct F3Params {
     const float* dw_w;
     const float* dw_b;
-    const float* bias;
-    float* C;
     int P, K, N, Ho, Wo;
     int TRt;                 // output rows per tile
     int TR;                  // output rows per input box
@@ -75,14 +76,15 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* map, uin
 template <int BN, int NSPLIT, int STRIDE, int R>
 __global__ void __launch_bounds__(kF3Threads, 1)
 sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_b_hi,
-                  const __grid_constant__ CUtensorMap map_b_lo, const F3Params prm) {
+                  const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_c,
+                  const __grid_constant__ BiasParam biasp, const F3Params prm) {
     using Cfg = F3Cfg<BN, NSPLIT>;
     constexpr int NC = (R - 1) * STRIDE + 3;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    unsigned char* in_ring = smem + kABStages * Cfg::kStageBytes;
-    float* epi_stage = reinterpret_cast<float*>(in_ring + prm.in_stages * prm.in_stride);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(epi_stage) + kEpiBytes);
+    unsigned char* epi_base = smem + kABStages * Cfg::kStageBytes;           // 1024-byte aligned (swizzled store blocks)
+    unsigned char* in_ring = epi_base + kEpiBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(in_ring + prm.in_stages * prm.in_stride);
     uint64_t* full_bar = bars;                          // [2]  A (stencil) + B (TMA) ready
     uint64_t* empty_bar = bars + 2;                     // [2]  MMAs of the stage retired
     uint64_t* in_full = bars + 4;                       // [6]
@@ -104,7 +106,10 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
         tma_prefetch_desc(&map_b_hi);
         if (NSPLIT > 1) tma_prefetch_desc(&map_b_lo);
     }
-    if (warp == 3 && lane == 0) tma_prefetch_desc(&map_in);
+    if (warp == 3 && lane == 0) {
+        tma_prefetch_desc(&map_in);
+        tma_prefetch_desc(&map_c);
+    }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kABStages; ++i) {
             mbar_init(&full_bar[i], 1 + kF3ProdWarps);
@@ -305,51 +310,49 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
     } else if (warp >= 4) {
         // ================================================================= epilogue
         const int q = warp & 3;
+        const uint32_t stg = smem_u32(epi_base) + static_cast<uint32_t>(q * kEpiBufBytes);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const int m_tile = t / n_tiles, n_blk = t - m_tile * n_tiles;
             const int p = m_tile / prm.tiles_per_patch;
             const int oh0 = (m_tile - p * prm.tiles_per_patch) * prm.TRt;
-            const long long mbase = (static_cast<long long>(p) * Ho + oh0) * Wo;
+            const int row0 = (p * Ho + oh0) * Wo + q * 32;               // < 2^31: checked by the launcher
             mbar_wait_sleepy(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const int n0 = n_blk * BN;
-            const uint32_t stg = smem_u32(epi_stage) + static_cast<uint32_t>(q * 32 * kEpiStride * 4);
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
-            const int srow = lane >> 3, scol = (lane & 7) * 4;
-            if (q * 32 < valid_rows) {
+            if (q * 32 < valid_rows) {                                   // valid_rows is a multiple of 32
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), r);
+                    if (lane == 0) tma_store_wait_read<0>();          // previous block's store has read the buffer
+                    __syncwarp();
                     tmem_ld_wait();
+                    const float* bp = biasp.v + n0 + c0;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4*>(prm.bias + n0 + c0 + j));
+                    for (int j = 0; j < 8; ++j) {
                         float4 o;
-                        o.x = fmaxf(fmaf(__uint_as_float(r[j + 0]), prm.out_scale, bv.x), 0.f);
-                        o.y = fmaxf(fmaf(__uint_as_float(r[j + 1]), prm.out_scale, bv.y), 0.f);
-                        o.z = fmaxf(fmaf(__uint_as_float(r[j + 2]), prm.out_scale, bv.z), 0.f);
-                        o.w = fmaxf(fmaf(__uint_as_float(r[j + 3]), prm.out_scale, bv.w), 0.f);
-                        sts128(stg + static_cast<uint32_t>((lane * kEpiStride + j) * 4), o);
+                        o.x = fmaxf(fmaf(__uint_as_float(r[4 * j + 0]), prm.out_scale, bp[4 * j + 0]), 0.f);
+                        o.y = fmaxf(fmaf(__uint_as_float(r[4 * j + 1]), prm.out_scale, bp[4 * j + 1]), 0.f);
+                        o.z = fmaxf(fmaf(__uint_as_float(r[4 * j + 2]), prm.out_scale, bp[4 * j + 2]), 0.f);
+                        o.w = fmaxf(fmaf(__uint_as_float(r[4 * j + 3]), prm.out_scale, bp[4 * j + 3]), 0.f);
+                        sts128(epi_swz_addr(stg, lane, j), o);
                     }
+                    fence_proxy_async_smem();
                     __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int rl = i * 4 + srow;
-                        const float4 o = lds128(stg + static_cast<uint32_t>((rl * kEpiStride + scol) * 4));
-                        const int lrow = q * 32 + rl;
-                        if (lrow < valid_rows)
-                            *reinterpret_cast<float4*>(prm.C + (mbase + lrow) * N + n0 + c0 + scol) = o;
+                    if (lane == 0) {
+                        tma_store_2d(&map_c, stg, n0 + c0, row0);
+                        tma_store_commit();
                     }
-                    __syncwarp();
                 }
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (lane == 0) tma_store_wait_all();
     }
 
     tc_fence_before();
@@ -376,9 +379,9 @@ bool encode_4d_f32(CUtensorMap* map, const float* ptr, int C, int W, int H, int 
 }
 
 template <int BN, int NSPLIT, int STRIDE, int R>
-cudaError_t launch_f3_t(const CUtensorMap& map_in, const PwGemmPlan& p, const F3Params& prm, int smem_bytes, int grid,
-                        cudaStream_t stream) {
-    sep_fused3_kernel<BN, NSPLIT, STRIDE, R><<<grid, kF3Threads, smem_bytes, stream>>>(map_in, p.b_hi, p.b_lo, prm);
+cudaError_t launch_f3_t(const CUtensorMap& map_in, const CUtensorMap& map_c, const BiasParam& bp, const PwGemmPlan& p,
+                        const F3Params& prm, int smem_bytes, int grid, cudaStream_t stream) {
+    sep_fused3_kernel<BN, NSPLIT, STRIDE, R><<<grid, kF3Threads, smem_bytes, stream>>>(map_in, p.b_hi, p.b_lo, map_c, bp, prm);
     return cudaGetLastError();
 }
 
@@ -405,25 +408,25 @@ cudaError_t sep_fused3_init_device() {
 }
 
 bool sep_fused3_supported(int K, int N, int H, int W, int stride) {
-    if (K % kBK != 0 || N % 64 != 0) return false;
+    if (K % kBK != 0 || N % 64 != 0 || N > kMaxN) return false;
     if (stride != 1 && stride != 2) return false;
     if ((H % stride) || (W % stride)) return false;
     const int Ho = H / stride, Wo = W / stride;
     if (Wo < 4 || (Wo & (Wo - 1)) || Wo > kBM) return false;
     const int trt = Ho < kBM / Wo ? Ho : kBM / Wo;
-    if (trt < 1 || Ho % trt) return false;
+    if (trt < 1 || Ho % trt || (trt * Wo) % 32) return false;       // epilogue stores whole 32-row blocks
     return true;
 }
 
 cudaError_t launch_sep_fused3(const PwGemmPlan& p, const float* X, const float* dw_w, const float* dw_b,
-                              const float* bias, float* C, int P, int H, int W, int stride, int num_sms,
+                              const float* bias_host, float* C, int P, int H, int W, int stride, int num_sms,
                               cudaStream_t stream) {
     if (P <= 0) return cudaSuccess;
-    if (!sep_fused3_supported(p.K, p.N, H, W, stride)) return cudaErrorInvalidValue;
+    if (!sep_fused3_supported(p.K, p.N, H, W, stride) || bias_host == nullptr) return cudaErrorInvalidValue;
     if (p.block_n != 64 && p.block_n != 128) return cudaErrorInvalidValue;
     const int Ho = H / stride, Wo = W / stride;
     F3Params prm;
-    prm.dw_w = dw_w; prm.dw_b = dw_b; prm.bias = bias; prm.C = C;
+    prm.dw_w = dw_w; prm.dw_b = dw_b;
     prm.P = P; prm.K = p.K; prm.N = p.N; prm.Ho = Ho; prm.Wo = Wo;
     prm.TRt = Ho < kBM / Wo ? Ho : kBM / Wo;
     prm.tiles_per_patch = Ho / prm.TRt;
@@ -450,14 +453,18 @@ cudaError_t launch_sep_fused3(const PwGemmPlan& p, const float* X, const float* 
     const long long tiles = static_cast<long long>(P) * prm.tiles_per_patch * (p.N / p.block_n);
     if (tiles >= (1LL << 31)) return cudaErrorInvalidValue;
     const int grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
-    CUtensorMap map_in;
+    CUtensorMap map_in, map_c;
     if (!encode_4d_f32(&map_in, X, p.K, W, H, P, kCB, prm.BW, prm.BH)) return cudaErrorUnknown;
+    const long long m_rows = static_cast<long long>(P) * Ho * Wo;
+    if (m_rows >= (1LL << 31) || !encode_store_map_f32(&map_c, C, m_rows, p.N)) return cudaErrorUnknown;
+    BiasParam bp;
+    for (int i = 0; i < kMaxN; ++i) bp.v[i] = i < p.N ? bias_host[i] : 0.f;
 #define BD_F3(BN, NS)                                                                                              \
     do {                                                                                                           \
-        if (stride == 1) return R == 4 ? launch_f3_t<BN, NS, 1, 4>(map_in, p, prm, smem_bytes, grid, stream)       \
-                                       : launch_f3_t<BN, NS, 1, 2>(map_in, p, prm, smem_bytes, grid, stream);      \
-        return R == 4 ? launch_f3_t<BN, NS, 2, 4>(map_in, p, prm, smem_bytes, grid, stream)                        \
-                      : launch_f3_t<BN, NS, 2, 2>(map_in, p, prm, smem_bytes, grid, stream);                       \
+        if (stride == 1) return R == 4 ? launch_f3_t<BN, NS, 1, 4>(map_in, map_c, bp, p, prm, smem_bytes, grid, stream)       \
+                                       : launch_f3_t<BN, NS, 1, 2>(map_in, map_c, bp, p, prm, smem_bytes, grid, stream);      \
+        return R == 4 ? launch_f3_t<BN, NS, 2, 4>(map_in, map_c, bp, p, prm, smem_bytes, grid, stream)                        \
+                      : launch_f3_t<BN, NS, 2, 2>(map_in, map_c, bp, p, prm, smem_bytes, grid, stream);                       \
     } while (0)
     if (p.nsplit == 1) {
         if (p.block_n == 64) BD_F3(64, 1);

@@ -133,6 +133,7 @@ def _median_threshold(a):
     ("fp16x3", 96, 199.68, -1), ("fp16", 96, 61.3, -1), ("fp16x3", 96, 61.3, 0), ("fp16x3", 48, 33.1, 0x7FF),
     ("fp16x3", 48, 33.1, 0x10002), ("fp16", 96, 20.0, 0x20000), ("fp16x3", 96, 61.3, 0x5003E),
     ("fp16x3", 48, 33.1, 0x507FF), ("fp16x3", 96, 61.3, 0xC0006), ("fp16x3", 48, 33.1, 0xC0006),
+    ("fp16x3", 96, 61.3, 0x10002),
 ])
 def test_predict_matches_oracle(engines, yamnet_variables, mel, head, precision, hop, seconds, fuse_mask):
     e = engines(precision, early_patches=16, late_patches=48, fuse_mask=fuse_mask)   # several early / late sub-batches
@@ -225,11 +226,11 @@ def test_device_resident_entry_point(engines):
     assert P == want.shape[0]
     assert np.array_equal(dact.cpu().numpy(), want)
     prof = e.profile_device_ptr(dx.data_ptr(), dx.numel(), 96)
-    # defaults: layer 1 + layer-2 depthwise share a kernel (counted as conv1), layer 3 runs fused with its pointwise
-    assert prof["pointwise"]["launches"] == 13 and prof["depthwise"]["launches"] == 11
+    # defaults: layers 1+2 run as one kernel (counted as conv1), layers 3..6 run fused with their pointwise
+    assert prof["pointwise"]["launches"] == 12 and prof["depthwise"]["launches"] == 8
     assert all(prof[k]["ms"] > 0 for k in ("frontend", "conv1", "depthwise", "pointwise", "pool_head"))
-    assert [v["pw_launches"] for v in prof["layers"].values()] == [1] * 13
-    assert [v["dw_launches"] for v in prof["layers"].values()] == [0, 0] + [1] * 11
+    assert [v["pw_launches"] for v in prof["layers"].values()] == [0] + [1] * 12
+    assert [v["dw_launches"] for v in prof["layers"].values()] == [0] * 5 + [1] * 8
 
 
 # ------------------------------------------------------------------------------------------------ full-size properties
