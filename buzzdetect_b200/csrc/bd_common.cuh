@@ -5,6 +5,9 @@
 #include <cstdint>
 #include <cstdio>
 
+#ifndef BD_SLEEP_HINT_NS
+#define BD_SLEEP_HINT_NS 20000u
+#endif
 #ifndef BD_SPIN_LIMIT
 // Bounded mbarrier spins: a mis-programmed pipeline traps instead of hanging the GPU box.
 #define BD_SPIN_LIMIT (1u << 26)
@@ -59,7 +62,7 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
 }
 __device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
-    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    while (!mbar_try_wait_hint(bar, parity, BD_SLEEP_HINT_NS)) {
         if (++spins > (1u << 22)) {
             printf("bd: mbarrier timeout block %d thread %d\n", (int)blockIdx.x, (int)threadIdx.x);
             __trap();
@@ -72,6 +75,18 @@ __device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity)
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+// predicated form: zeros when `pred` is false (no branch: the load itself is predicated)
+__device__ __forceinline__ float4 lds128_pred(uint32_t addr, bool pred) {
+    float4 v;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\tmov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t"
+        "@p ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+        : "r"(addr), "r"(static_cast<uint32_t>(pred)));
     return v;
 }
 __device__ __forceinline__ void sts128(uint32_t addr, float4 v) {

@@ -62,6 +62,7 @@ cudaError_t launch_pool_head(const float* y, int P, int rows_per_patch, const fl
 // ---- pw_gemm_sm100.cu  (tcgen05 / TMEM / TMA)
 struct PwGemmPlan {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    CUtensorMap b64_hi, b64_lo;   // the same weight planes in 64-row boxes (sep_fused3_kernel's 16 KB ring slots)
     int M_max, N, K, block_n, nsplit;
     float out_scale;   // accumulators are multiplied by this before the bias (weights are stored pre-scaled by 1/out_scale)
 };
@@ -94,8 +95,9 @@ typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint3
                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 TensorMapEncodeFn tensor_map_encode_fn();
-// Store map for a row-major float32 [rows, cols] output written in [32 x 32] SWIZZLE_128B blocks (epi_swz_addr).
-bool encode_store_map_f32(CUtensorMap* map, float* ptr, long long rows, int cols);
+// Store map for a row-major float32 [rows, cols] output written in [box_rows x 32] SWIZZLE_128B blocks (epi_swz_addr);
+// box_rows = 32, or 8 for the partial lane quad of a tile whose row count is not a multiple of 32.
+bool encode_store_map_f32(CUtensorMap* map, float* ptr, long long rows, int cols, int box_rows);
 
 // ---- sep_fused_sm100.cu  (fused separable block v3: TMA-staged depthwise input, see the file header)
 cudaError_t sep_fused3_init_device();

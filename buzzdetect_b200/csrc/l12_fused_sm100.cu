@@ -387,7 +387,7 @@ cudaError_t launch_l12_fused2(const PwGemmPlan& p, const float* logmel, int hop_
     if (tiles * kBM >= (1LL << 31)) return cudaErrorInvalidValue;
     const int grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
     CUtensorMap map_c;
-    if (!encode_store_map_f32(&map_c, C, tiles * kBM, 64)) return cudaErrorUnknown;
+    if (!encode_store_map_f32(&map_c, C, tiles * kBM, 64, 32)) return cudaErrorUnknown;
     Bias64 bp;
     for (int i = 0; i < 64; ++i) bp.v[i] = bias_host[i];
     if (p.nsplit == 1)

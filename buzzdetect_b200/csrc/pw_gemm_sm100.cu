@@ -759,12 +759,12 @@ TensorMapEncodeFn tensor_map_encode_fn() {
     return fn;
 }
 
-bool encode_store_map_f32(CUtensorMap* map, float* ptr, long long rows, int cols) {
+bool encode_store_map_f32(CUtensorMap* map, float* ptr, long long rows, int cols, int box_rows) {
     TensorMapEncodeFn fn = tensor_map_encode_fn();
-    if (fn == nullptr || cols % 32 != 0 || rows < 1) return false;
+    if (fn == nullptr || cols % 32 != 0 || rows < 1 || box_rows < 8 || box_rows % 8) return false;
     cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
     cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * 4};
-    cuuint32_t box[2] = {32, 32};
+    cuuint32_t box[2] = {32, static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -861,7 +861,8 @@ cudaError_t pw_gemm_make_plan(PwGemmPlan* plan, const __half* a_hi, const __half
     if (a_lo == nullptr) a_lo = a_hi;
     if (b_lo == nullptr) b_lo = b_hi;
     if (!encode_2d_f16(&plan->a_hi, a_hi, M_max, K, kBM) || !encode_2d_f16(&plan->a_lo, a_lo, M_max, K, kBM) ||
-        !encode_2d_f16(&plan->b_hi, b_hi, N, K, bn) || !encode_2d_f16(&plan->b_lo, b_lo, N, K, bn)) {
+        !encode_2d_f16(&plan->b_hi, b_hi, N, K, bn) || !encode_2d_f16(&plan->b_lo, b_lo, N, K, bn) ||
+        !encode_2d_f16(&plan->b64_hi, b_hi, N, K, 64) || !encode_2d_f16(&plan->b64_lo, b_lo, N, K, 64)) {
         *err = "cuTensorMapEncodeTiled failed";
         return cudaErrorUnknown;
     }

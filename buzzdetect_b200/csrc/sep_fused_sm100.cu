@@ -1,25 +1,29 @@
-// Fused separable block, version 3 (sm_100a): depthwise 3x3 + BN + ReLU -> pointwise 1x1 + BN + ReLU in ONE kernel,
-// with the depthwise INPUT staged through shared memory by TMA.
+// Fused separable block (sm_100a): depthwise 3x3 + BN + ReLU -> pointwise 1x1 + BN + ReLU in ONE kernel, with the
+// depthwise INPUT staged through shared memory by TMA and the pointwise accumulators for up to 512 output channels
+// resident in TMEM, so the stencil runs ONCE per output tile whatever the layer width.
 //     C[M,N] = relu( relu(DW3x3(X) + b_dw)[M,K] * W[N,K]^T * out_scale + b_pw )
 // Reference op: _separable_conv, embedders/yamnet/yamnet.py:52-74 (BN folded on the host).
 //
-// Why a third version: sep_fused_kernel (pw_gemm_sm100.cu) feeds its stencil from registers, so every producer thread
-// exposes a full DRAM round trip per strip and the kernel is latency bound (profiles/fusion_r1.md).  Here a dedicated
-// thread streams 4-D TMA boxes  [32 channels, BW columns, BH rows, 1 patch]  of the float32 NHWC input into a ring of
-// shared-memory tiles, several boxes ahead of the stencil warps.  The box starts one pixel outside the image for
-// stride 1 (pad 1/1) and ends one pixel outside for stride 2 (TensorFlow SAME on even sizes pads 0/1); TMA zero-fills
-// out-of-bounds elements, so the stencil has no boundary tests at all.
+// Data flow per CTA (512 threads, one CTA per SM, persistent over output tiles):
+//   warp 3      input TMA: 4-D boxes [32 channels, BW columns, BH rows, PB patches] of the float32 NHWC input into a ring
+//               of shared-memory tiles, several boxes ahead of the stencil.  A box starts one pixel outside the image
+//               for stride 1 (pad 1/1) and ends one pixel outside for stride 2 (TensorFlow SAME on even sizes pads
+//               0/1); TMA zero-fills out-of-bounds elements, so the stencil has no boundary tests.
+//   warps 8-15  stencil: two groups of four warps take alternate boxes; a thread owns 4 channels of a 4x2 (stride 1)
+//               or 2x2 (stride 2) block of output pixels (3 / 6.25 LDS.128 per output vector), and writes hi/lo fp16
+//               straight into the SWIZZLE_128B K-major A tile (2 stages of 128 rows x 64 channels).
+//   warp 0      weight TMA: 64-row x 64-channel boxes of the hi/lo weight planes into a ring of 16 KB slots.
+//   warp 1      tcgen05.mma issuer: per k-block, NACC/64 weight slots x 4 k-steps x (1 | 3) MMAs (M=128, N=64, K=16)
+//               into TMEM columns [slot*64, +64) -- the A tile is read NACC/64 times, the stencil computed once.
+//   warp 2      TMEM allocator: NACC <= 256: two accumulator stages; NACC = 512: one stage = all 512 columns.
+//   warps 4-7   epilogue: tcgen05.ld -> scale + bias (constant bank) + ReLU -> swizzled smem block -> TMA store.
 //
-// Warp roles (512 threads, one CTA per SM, persistent over output tiles):
-//   warp 0      weight TMA (SWIZZLE_128B K-major boxes, as in pw_gemm_kernel)
-//   warp 1      tcgen05.mma issuer (M=128, N=BN, K=16; 3 MMAs per k-step in the fp16x3 split mode)
-//   warp 2      TMEM allocator
-//   warp 3      input TMA (float32 boxes -> in_ring)
-//   warps 4-7   epilogue: tcgen05.ld -> scale + bias (constant bank) + ReLU -> swizzled smem block -> TMA store
-//   warps 8-15  stencil producers: depthwise from in_ring, hi/lo fp16 straight into the swizzled A tile
+// An output tile is either TRt image rows x Wo columns of ONE patch, or PT WHOLE patches (6x4 layers: 5 patches =
+// 120 of the 128 accumulator rows), so tiles never cut a patch and one box covers a tile's input.
 //
-// An output tile is TRt image rows x Wo columns of ONE patch (<= 128 pixels, so tiles never straddle patches and one
-// box covers a tile's input); layers whose patch has 96 output pixels run with 96 of the 128 accumulator rows live.
+// Why these choices (measured, profiles/r1_summary.md): the kernels of this family are bound by the SM's L1/shared
+// data pipe (one 128-byte wavefront per clock), not by HBM or FMA issue -- hence block-shaped stencils, bias from the
+// constant bank, and TMA stores instead of LDS + STG in the epilogue.
 #include "bd_common.cuh"
 #include "bd_kernels.cuh"
 
@@ -30,37 +34,41 @@ namespace {
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kCB = 32;                                          // channels per input box (128-byte pixel rows)
+constexpr int kBNs = 64;                                         // weight rows per ring slot = MMA N
 constexpr int kF3Threads = 512;
-constexpr int kF3ProdWarps = 8;
-constexpr int kF3ProdThreads = kF3ProdWarps * 32;
+constexpr int kGroupThreads = 128;                               // stencil group = 4 warps
 constexpr int kEpiBufBytes = 32 * 128;                           // one [32 rows x 32 float] swizzled block per epilogue warp
 constexpr int kEpiBytes = 4 * kEpiBufBytes;
+constexpr int kAStages = 2;
+constexpr int kMaxInStages = 6;
+constexpr int kMaxBSlots = 8;
+constexpr int kSmemMax = 227 * 1024;
+constexpr int kBarBytes = 320;
 constexpr int kMaxN = 512;
+constexpr int kATile = kBM * kBK * 2;                            // one fp16 plane of the A tile, 16 KB
+constexpr int kBSlotPlane = kBNs * kBK * 2;                      // 8 KB
 
 struct BiasParam { float v[kMaxN]; };                            // kernel parameter = constant bank (no L1 traffic)
-constexpr int kABStages = 2;
-constexpr int kMaxInStages = 6;
-constexpr int kSmemMax = 227 * 1024;
-constexpr int kBarBytes = 256;
-
-template <int BN, int NSPLIT>
-struct F3Cfg {
-    static constexpr int kPlanes = NSPLIT == 1 ? 1 : 2;
-    static constexpr int kATile = kBM * kBK * 2;
-    static constexpr int kBTile = BN * kBK * 2;
-    static constexpr int kStageBytes = kPlanes * (kATile + kBTile);
-    static constexpr int kTmemCols = 2 * BN;
-};
 
 struct F3Params {
     const float* dw_w;
     const float* dw_b;
     int P, K, N, Ho, Wo;
-    int TRt;                 // output rows per tile
-    int TR;                  // output rows per input box
-    int BW, BH;              // box extent in input pixels
-    int tiles_per_patch;
-    int in_stages, in_stride;   // ring depth, bytes between ring slots
+    int PT;                  // patches per tile (1, or whole patches when > 1)
+    int TRt;                 // output rows per tile (PT == 1) or Ho
+    int PB, TR;              // patches / output rows per input box
+    int BW, BH;              // box extent in input pixels (per patch)
+    int parts;               // boxes per (tile, 32-channel group)
+    int rows_per_part;       // A-tile rows produced from one box
+    int valid_rows;          // live accumulator rows per tile
+    int tiles_per_patch;     // PT == 1
+    int m_tiles;
+    int in_stages, in_stride;   // input ring depth, bytes between slots
+    int b_slots;
+    int nohalo;              // 1: boxes hold whole patches without the padding ring; the stencil masks its border taps
+    int H, W;                // input extent per patch
+    int items;               // stencil blocks per box (x 8 channel quads)
+    int blocks_w, blocks_h;  // stencil blocks per patch-part in W and H
     float out_scale;
 };
 
@@ -73,34 +81,69 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* map, uin
         : "memory");
 }
 
-template <int BN, int NSPLIT, int STRIDE, int R>
+// hi/lo fp16 of 4 channels of one pixel -> the swizzled A tile (row = pixel, 128-byte rows, 16-byte chunks XOR row&7)
+template <int NSPLIT>
+__device__ __forceinline__ void store_a(uint32_t a_hi, uint32_t a_lo, uint32_t row, uint32_t chunk, uint32_t half8, float4 a) {
+    a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+    const uint32_t off = (row >> 3) * 1024u + (row & 7u) * 128u + ((chunk ^ (row & 7u)) << 4) + half8;
+    const __half h0 = __float2half_rn(a.x), h1 = __float2half_rn(a.y);
+    const __half h2 = __float2half_rn(a.z), h3 = __float2half_rn(a.w);
+    __half2 hp[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
+    sts64(a_hi + off, reinterpret_cast<uint32_t*>(hp)[0], reinterpret_cast<uint32_t*>(hp)[1]);
+    if (NSPLIT > 1) {
+        __half2 lp[2] = {__halves2half2(__float2half_rn(a.x - __half2float(h0)), __float2half_rn(a.y - __half2float(h1))),
+                         __halves2half2(__float2half_rn(a.z - __half2float(h2)), __float2half_rn(a.w - __half2float(h3)))};
+        sts64(a_lo + off, reinterpret_cast<uint32_t*>(lp)[0], reinterpret_cast<uint32_t*>(lp)[1]);
+    }
+}
+
+__device__ __forceinline__ void fma4(float4& acc, const float4& x, const float4& w) {
+    acc.x = fmaf(x.x, w.x, acc.x);
+    acc.y = fmaf(x.y, w.y, acc.y);
+    acc.z = fmaf(x.z, w.z, acc.z);
+    acc.w = fmaf(x.w, w.w, acc.w);
+}
+
+template <int NSPLIT, int STRIDE, int NACC, bool NOHALO>
 __global__ void __launch_bounds__(kF3Threads, 1)
 sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_b_hi,
                   const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_c,
-                  const __grid_constant__ BiasParam biasp, const F3Params prm) {
-    using Cfg = F3Cfg<BN, NSPLIT>;
-    constexpr int NC = (R - 1) * STRIDE + 3;
+                  const __grid_constant__ CUtensorMap map_c8, const __grid_constant__ BiasParam biasp,
+                  const F3Params prm) {
+    constexpr int kPlanes = NSPLIT == 1 ? 1 : 2;
+    constexpr int kAStageBytes = kPlanes * kATile;
+    constexpr int kBSlotBytes = kPlanes * kBSlotPlane;
+    constexpr int kAccStages = NACC == 512 ? 1 : 2;
+    constexpr int kTmemCols = NACC == 128 ? 256 : 512;
+    constexpr int kSlotsPerKb = NACC / kBNs;
+    constexpr int BWc = STRIDE == 1 ? 4 : 2;            // stencil block: BWc columns x 2 rows of output pixels
+    constexpr int NCW = (BWc - 1) * STRIDE + 3;         // input columns per block row
+    constexpr int NRW = STRIDE + 3;                     // input rows per block (2 output rows)
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    unsigned char* epi_base = smem + kABStages * Cfg::kStageBytes;           // 1024-byte aligned (swizzled store blocks)
-    unsigned char* in_ring = epi_base + kEpiBytes;
+    unsigned char* a_base = smem;                                            // [2][planes][16 KB]
+    unsigned char* epi_base = a_base + kAStages * kAStageBytes;              // [4 warps][4 KB], 1024-byte aligned
+    unsigned char* b_base = epi_base + kEpiBytes;                            // [b_slots][planes][8 KB]
+    unsigned char* in_ring = b_base + prm.b_slots * kBSlotBytes;             // [in_stages][in_stride]
     uint64_t* bars = reinterpret_cast<uint64_t*>(in_ring + prm.in_stages * prm.in_stride);
-    uint64_t* full_bar = bars;                          // [2]  A (stencil) + B (TMA) ready
-    uint64_t* empty_bar = bars + 2;                     // [2]  MMAs of the stage retired
-    uint64_t* in_full = bars + 4;                       // [6]
-    uint64_t* in_empty = bars + 10;                     // [6]
-    uint64_t* tmem_full = bars + 16;                    // [2]
-    uint64_t* tmem_empty = bars + 18;                   // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    uint64_t* a_full = bars;                            // [2]
+    uint64_t* a_empty = bars + 2;                       // [2]
+    uint64_t* b_full = bars + 4;                        // [8]
+    uint64_t* b_empty = bars + 12;                      // [8]
+    uint64_t* in_full = bars + 20;                      // [6]
+    uint64_t* in_empty = bars + 26;                     // [6]
+    uint64_t* tmem_full = bars + 32;                    // [2]
+    uint64_t* tmem_empty = bars + 34;                   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int K = prm.K, N = prm.N, Ho = prm.Ho, Wo = prm.Wo;
-    const int n_tiles = N / BN;
-    const int num_tiles = prm.P * prm.tiles_per_patch * n_tiles;
+    const int K = prm.K, Ho = prm.Ho, Wo = prm.Wo;
+    const int n_groups = prm.N / NACC;
+    const int num_pass = prm.m_tiles * n_groups;        // a pass = (output tile, group of NACC output channels)
     const int num_kb = K / kBK;
-    const int parts = prm.TRt / prm.TR;
-    const int valid_rows = prm.TRt * Wo;
+    const int parts = prm.parts;
     const int in_stages = prm.in_stages;
+    const int b_slots = prm.b_slots;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_b_hi);
@@ -109,15 +152,20 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
     if (warp == 3 && lane == 0) {
         tma_prefetch_desc(&map_in);
         tma_prefetch_desc(&map_c);
+        tma_prefetch_desc(&map_c8);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < kABStages; ++i) {
-            mbar_init(&full_bar[i], 1 + kF3ProdWarps);
-            mbar_init(&empty_bar[i], 1);
+        for (int i = 0; i < kAStages; ++i) {
+            mbar_init(&a_full[i], 8);                   // every stencil warp arrives once per k-block
+            mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < kMaxBSlots; ++i) {
+            mbar_init(&b_full[i], 1);
+            mbar_init(&b_empty[i], 1);
         }
         for (int i = 0; i < kMaxInStages; ++i) {
             mbar_init(&in_full[i], 1);
-            mbar_init(&in_empty[i], kF3ProdWarps);
+            mbar_init(&in_empty[i], 4);                 // the four warps of the consuming stencil group
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
@@ -125,14 +173,12 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
-    if (valid_rows < kBM) {
-        // rows the stencil never writes must not hold NaN/Inf bit patterns (their accumulator rows are discarded,
-        // but keep the tensor pipe away from garbage): zero both A stages once
-        for (int s = 0; s < kABStages; ++s) {
-            uint4* a = reinterpret_cast<uint4*>(smem + s * Cfg::kStageBytes);
-            for (int i = threadIdx.x; i < Cfg::kPlanes * Cfg::kATile / 16; i += kF3Threads) a[i] = make_uint4(0, 0, 0, 0);
-        }
+    if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+    if (prm.valid_rows < kBM) {
+        // rows the stencil never writes: zero both A stages once (their accumulator rows are discarded, but keep
+        // uninitialised bit patterns away from the tensor pipe)
+        uint4* a = reinterpret_cast<uint4*>(a_base);
+        for (int i = threadIdx.x; i < kAStages * kAStageBytes / 16; i += kF3Threads) a[i] = make_uint4(0, 0, 0, 0);
         fence_proxy_async_smem();
     }
     tc_fence_before();
@@ -143,38 +189,49 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
     if (warp == 0) {
         // ================================================================= weight TMA
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int n_blk = t % n_tiles;
+            int bs = 0;
+            uint32_t bphase = 0;
+            for (int ps = blockIdx.x; ps < num_pass; ps += gridDim.x) {
+                const int n0 = (ps % n_groups) * NACC;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    unsigned char* sb = smem + stage * Cfg::kStageBytes + Cfg::kPlanes * Cfg::kATile;
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kPlanes * Cfg::kBTile);
-                    tma_load_2d(sb, &map_b_hi, &full_bar[stage], kb * kBK, n_blk * BN);
-                    if (NSPLIT > 1) tma_load_2d(sb + Cfg::kBTile, &map_b_lo, &full_bar[stage], kb * kBK, n_blk * BN);
-                    if (++stage == kABStages) { stage = 0; phase ^= 1; }
+#pragma unroll 1
+                    for (int nb = 0; nb < kSlotsPerKb; ++nb) {
+                        mbar_wait(&b_empty[bs], bphase ^ 1);
+                        unsigned char* dst = b_base + bs * kBSlotBytes;
+                        mbar_arrive_expect_tx(&b_full[bs], kBSlotBytes);
+                        tma_load_2d(dst, &map_b_hi, &b_full[bs], kb * kBK, n0 + nb * kBNs);
+                        if (NSPLIT > 1) tma_load_2d(dst + kBSlotPlane, &map_b_lo, &b_full[bs], kb * kBK, n0 + nb * kBNs);
+                        if (++bs == b_slots) { bs = 0; bphase ^= 1; }
+                    }
                 }
             }
         }
     } else if (warp == 3) {
         // ================================================================= input TMA (float32 NHWC boxes)
         if (lane == 0) {
-            const uint32_t box_bytes = static_cast<uint32_t>(kCB * prm.BW * prm.BH * 4);
+            const uint32_t box_bytes = static_cast<uint32_t>(kCB * prm.BW * prm.BH * prm.PB * 4);
             int is = 0;
             uint32_t iphase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int m_tile = t / n_tiles;
-                const int p = m_tile / prm.tiles_per_patch;
-                const int oh0 = (m_tile - p * prm.tiles_per_patch) * prm.TRt;
+            for (int ps = blockIdx.x; ps < num_pass; ps += gridDim.x) {
+                const int m_tile = ps / n_groups;
+                int p0, oh0;
+                if (prm.PT == 1) {
+                    p0 = m_tile / prm.tiles_per_patch;
+                    oh0 = (m_tile - p0 * prm.tiles_per_patch) * prm.TRt;
+                } else {
+                    p0 = m_tile * prm.PT;
+                    oh0 = 0;
+                }
                 for (int kb = 0; kb < num_kb; ++kb) {
                     for (int sb = 0; sb < kBK / kCB; ++sb) {
                         for (int part = 0; part < parts; ++part) {
-                            const int oh = oh0 + part * prm.TR;
+                            const int oh = prm.PT == 1 ? oh0 + part * prm.TR : 0;
+                            const int pp = prm.PT == 1 ? p0 : p0 + part * prm.PB;
                             mbar_wait(&in_empty[is], iphase ^ 1);
                             mbar_arrive_expect_tx(&in_full[is], box_bytes);
                             tma_load_4d(in_ring + is * prm.in_stride, &map_in, &in_full[is], kb * kBK + sb * kCB,
-                                        STRIDE == 1 ? -1 : 0, STRIDE == 1 ? oh - 1 : 2 * oh, p);
+                                        (STRIDE == 1 && !NOHALO) ? -1 : 0,
+                                        NOHALO ? 0 : (STRIDE == 1 ? oh - 1 : 2 * oh), pp);
                             if (++is == in_stages) { is = 0; iphase ^= 1; }
                         }
                     }
@@ -184,153 +241,180 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
     } else if (warp == 1) {
         // ================================================================= MMA issuer
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(kBM, BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            constexpr uint32_t idesc = umma_idesc_f16(kBM, kBNs);
+            int stage = 0, bs = 0, acc = 0;
+            uint32_t phase = 0, bphase = 0, acc_phase = 0;
+            for (int ps = blockIdx.x; ps < num_pass; ps += gridDim.x) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+                const uint32_t d_acc = tmem_base + static_cast<uint32_t>(acc * NACC);
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
+                    mbar_wait(&a_full[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
-                    const uint32_t a_lo = a_hi + Cfg::kATile;
-                    const uint32_t b_hi = a_hi + Cfg::kPlanes * Cfg::kATile;
-                    const uint32_t b_lo = b_hi + Cfg::kBTile;
+                    const uint32_t a_hi = smem_u32(a_base + stage * kAStageBytes);
+                    const uint32_t a_lo = a_hi + kATile;
+#pragma unroll 1
+                    for (int nb = 0; nb < kSlotsPerKb; ++nb) {
+                        mbar_wait(&b_full[bs], bphase);
+                        tc_fence_after();
+                        const uint32_t b_hi = smem_u32(b_base + bs * kBSlotBytes);
+                        const uint32_t b_lo = b_hi + kBSlotPlane;
+                        const uint32_t d_tmem = d_acc + static_cast<uint32_t>(nb * kBNs);
 #pragma unroll
-                    for (int k = 0; k < kBK / 16; ++k) {
-                        const uint32_t koff = static_cast<uint32_t>(k) * 32u;
-                        const uint64_t da_hi = umma_desc_k128(a_hi + koff);
-                        const uint64_t db_hi = umma_desc_k128(b_hi + koff);
-                        umma_f16_ss(d_tmem, da_hi, db_hi, idesc, (kb | k) != 0 ? 1u : 0u);
-                        if (NSPLIT > 1) {
-                            const uint64_t da_lo = umma_desc_k128(a_lo + koff);
-                            const uint64_t db_lo = umma_desc_k128(b_lo + koff);
-                            umma_f16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
-                            umma_f16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
+                        for (int k = 0; k < kBK / 16; ++k) {
+                            const uint32_t koff = static_cast<uint32_t>(k) * 32u;
+                            const uint64_t da_hi = umma_desc_k128(a_hi + koff);
+                            const uint64_t db_hi = umma_desc_k128(b_hi + koff);
+                            umma_f16_ss(d_tmem, da_hi, db_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                            if (NSPLIT > 1) {
+                                const uint64_t da_lo = umma_desc_k128(a_lo + koff);
+                                const uint64_t db_lo = umma_desc_k128(b_lo + koff);
+                                umma_f16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
+                                umma_f16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
+                            }
                         }
+                        umma_commit(&b_empty[bs]);
+                        if (++bs == b_slots) { bs = 0; bphase ^= 1; }
                     }
-                    umma_commit(&empty_bar[stage]);
-                    if (++stage == kABStages) { stage = 0; phase ^= 1; }
+                    umma_commit(&a_empty[stage]);
+                    if (++stage == kAStages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tmem_full[acc]);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else if (warp >= 8) {
-        // ================================================================= stencil producers (smem -> smem A tile)
-        const int pt = threadIdx.x - 256;
-        const int quad = pt & 7;                        // 4 channels of the 32-channel box
-        const int strip0 = pt >> 3;                     // strips strip0, strip0 + 32, ...
-        const int wo_bits = 31 - __clz(Wo);
-        const int strips_per_box = (prm.TR * Wo) / R;
-        const int rowpitch = prm.BW * kCB * 4;          // bytes between box rows
+        // ================================================================= stencil (smem boxes -> smem A tile)
+        const int g = (warp - 8) >> 2;                  // group 0 / 1: alternate boxes
+        const int tg = threadIdx.x - 256 - g * kGroupThreads;
+        const int quad = tg & 7;                        // 4 channels of the 32-channel box
+        // this thread's (up to two) blocks of a box: input byte offset and first A-tile row, fixed for the kernel
+        // (whole-patch boxes carry no padding ring: taps outside the patch are masked instead -- bit i of rmask / bit c
+        // of cmask says whether window row i / column c exists)
+        uint32_t blk_in[2], blk_row[2], rmask[2], cmask[2];
+        bool blk_ok[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int item = tg + k * kGroupThreads;
+            blk_ok[k] = item < prm.items;
+            const int b = item >> 3;
+            const int bcol = b % prm.blocks_w;
+            const int b2 = b / prm.blocks_w;
+            const int brow = b2 % prm.blocks_h;
+            const int pl = b2 / prm.blocks_h;
+            const int pad = (NOHALO && STRIDE == 1) ? 1 : 0;
+            const int wr0 = 2 * brow * STRIDE - pad, wc0 = bcol * BWc * STRIDE - pad;     // window origin in box pixels
+            blk_in[k] = static_cast<uint32_t>((((pl * prm.BH + wr0) * prm.BW + wc0) * kCB + quad * 4) * 4);
+            blk_row[k] = static_cast<uint32_t>(pl * Ho * Wo + 2 * brow * Wo + bcol * BWc);
+            rmask[k] = cmask[k] = 0xFFFFFFFFu;
+            if (NOHALO) {
+                rmask[k] = cmask[k] = 0;
+                for (int i = 0; i < NRW; ++i) if (wr0 + i >= 0 && wr0 + i < prm.H) rmask[k] |= 1u << i;
+                for (int c = 0; c < NCW; ++c) if (wc0 + c >= 0 && wc0 + c < prm.W) cmask[k] |= 1u << c;
+            }
+        }
+        const uint32_t rowpitch = static_cast<uint32_t>(prm.BW * kCB * 4);     // bytes between box rows
         const uint32_t in_ring_u32 = smem_u32(in_ring);
-        int stage = 0, is = 0;
+        const uint32_t a_u32 = smem_u32(a_base);
+        const uint32_t half8 = static_cast<uint32_t>(quad & 1) << 3;
+        int stage = 0, is = g;
         uint32_t phase = 0, iphase = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        if (is >= in_stages) { is -= in_stages; iphase ^= 1; }
+        for (int ps = blockIdx.x; ps < num_pass; ps += gridDim.x) {
             for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait_sleepy(&empty_bar[stage], phase ^ 1);
-                const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
-                const uint32_t a_lo = a_hi + Cfg::kATile;
+                mbar_wait_sleepy(&a_empty[stage], phase ^ 1);
+                const uint32_t a_hi = a_u32 + static_cast<uint32_t>(stage * kAStageBytes);
+                const uint32_t a_lo = a_hi + kATile;
+                int sb_loaded = -1;
+                float4 kk[9], bdw;
 #pragma unroll 1
-                for (int sb = 0; sb < kBK / kCB; ++sb) {
-                    const int c = kb * kBK + sb * kCB + quad * 4;
-                    float4 kk[9];
+                for (int j = g; j < 2 * parts; j += 2) {
+                    const int sb = j / parts, part = j - sb * parts;
+                    if (sb != sb_loaded) {
+                        const int c = kb * kBK + sb * kCB + quad * 4;
 #pragma unroll
-                    for (int i = 0; i < 9; ++i) kk[i] = __ldg(reinterpret_cast<const float4*>(prm.dw_w + i * K + c));
-                    const float4 bdw = __ldg(reinterpret_cast<const float4*>(prm.dw_b + c));
+                        for (int i = 0; i < 9; ++i) kk[i] = __ldg(reinterpret_cast<const float4*>(prm.dw_w + i * K + c));
+                        bdw = __ldg(reinterpret_cast<const float4*>(prm.dw_b + c));
+                        sb_loaded = sb;
+                    }
                     const uint32_t chunk = static_cast<uint32_t>(sb * 4 + (quad >> 1));
+                    mbar_wait_sleepy(&in_full[is], iphase);
+                    const uint32_t tile = in_ring_u32 + static_cast<uint32_t>(is * prm.in_stride);
+                    const uint32_t part_row = static_cast<uint32_t>(part * prm.rows_per_part);
 #pragma unroll 1
-                    for (int part = 0; part < parts; ++part) {
-                        mbar_wait_sleepy(&in_full[is], iphase);
-                        const uint32_t tile = in_ring_u32 + static_cast<uint32_t>(is * prm.in_stride + quad * 16);
-#pragma unroll 1
-                        for (int strip = strip0; strip < strips_per_box; strip += kF3ProdThreads / 8) {
-                            const int px = strip * R;                     // box-local output pixel
-                            const int oh_l = px >> wo_bits, ow0 = px & (Wo - 1);
-                            const uint32_t base = tile + static_cast<uint32_t>((oh_l * STRIDE * prm.BW + ow0 * STRIDE) * kCB * 4);
-                            float4 acc[R];
+                    for (int k = 0; k < 2; ++k) {
+                        if (!blk_ok[k]) break;
+                        const uint32_t base = tile + blk_in[k];
+                        float4 acc[2][BWc];
 #pragma unroll
-                            for (int r = 0; r < R; ++r) acc[r] = bdw;
+                        for (int o = 0; o < 2; ++o)
 #pragma unroll
-                            for (int kh = 0; kh < 3; ++kh) {
-                                const uint32_t rowp = base + static_cast<uint32_t>(kh * rowpitch);
-                                float4 v[NC];
+                            for (int r = 0; r < BWc; ++r) acc[o][r] = bdw;
 #pragma unroll
-                                for (int j = 0; j < NC; ++j) v[j] = lds128(rowp + j * kCB * 4);
+                        for (int i = 0; i < NRW; ++i) {
+                            float4 v[NCW];
+                            const bool r_ok = (rmask[k] >> i) & 1u;
 #pragma unroll
-                                for (int r = 0; r < R; ++r) {
-#pragma unroll
-                                    for (int kw = 0; kw < 3; ++kw) {
-                                        const float4 x = v[r * STRIDE + kw];
-                                        const float4 w4 = kk[kh * 3 + kw];
-                                        acc[r].x = fmaf(x.x, w4.x, acc[r].x);
-                                        acc[r].y = fmaf(x.y, w4.y, acc[r].y);
-                                        acc[r].z = fmaf(x.z, w4.z, acc[r].z);
-                                        acc[r].w = fmaf(x.w, w4.w, acc[r].w);
-                                    }
-                                }
+                            for (int c = 0; c < NCW; ++c) {
+                                const uint32_t addr = base + i * rowpitch + c * (kCB * 4);
+                                v[c] = NOHALO ? lds128_pred(addr, r_ok && ((cmask[k] >> c) & 1u)) : lds128(addr);
                             }
-                            const int row0 = part * prm.TR * Wo + px;     // tile-local A row of the strip's first pixel
 #pragma unroll
-                            for (int r = 0; r < R; ++r) {
-                                float4 a = acc[r];
-                                a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
-                                const uint32_t row = static_cast<uint32_t>(row0 + r);
-                                const uint32_t off = (row >> 3) * 1024u + (row & 7u) * 128u + ((chunk ^ (row & 7u)) << 4) +
-                                                     (static_cast<uint32_t>(quad & 1) << 3);
-                                const __half h0 = __float2half_rn(a.x), h1 = __float2half_rn(a.y);
-                                const __half h2 = __float2half_rn(a.z), h3 = __float2half_rn(a.w);
-                                __half2 hp[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
-                                sts64(a_hi + off, reinterpret_cast<uint32_t*>(hp)[0], reinterpret_cast<uint32_t*>(hp)[1]);
-                                if (NSPLIT > 1) {
-                                    __half2 lp[2] = {__halves2half2(__float2half_rn(a.x - __half2float(h0)),
-                                                                    __float2half_rn(a.y - __half2float(h1))),
-                                                     __halves2half2(__float2half_rn(a.z - __half2float(h2)),
-                                                                    __float2half_rn(a.w - __half2float(h3)))};
-                                    sts64(a_lo + off, reinterpret_cast<uint32_t*>(lp)[0], reinterpret_cast<uint32_t*>(lp)[1]);
-                                }
+                            for (int o = 0; o < 2; ++o) {
+                                const int kh = i - o * STRIDE;
+                                if (kh < 0 || kh > 2) continue;
+#pragma unroll
+                                for (int r = 0; r < BWc; ++r)
+#pragma unroll
+                                    for (int kw = 0; kw < 3; ++kw) fma4(acc[o][r], v[r * STRIDE + kw], kk[kh * 3 + kw]);
                             }
                         }
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&in_empty[is]);           // box consumed (release orders the reads)
-                        if (++is == in_stages) { is = 0; iphase ^= 1; }
+                        const uint32_t row0 = part_row + blk_row[k];
+#pragma unroll
+                        for (int o = 0; o < 2; ++o)
+#pragma unroll
+                            for (int r = 0; r < BWc; ++r)
+                                store_a<NSPLIT>(a_hi, a_lo, row0 + static_cast<uint32_t>(o * Wo + r), chunk, half8, acc[o][r]);
                     }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&in_empty[is]);               // box consumed (release orders the reads)
+                    is += 2;
+                    if (is >= in_stages) { is -= in_stages; iphase ^= 1; }
                 }
                 fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the tensor-core proxy
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full_bar[stage]);
-                if (++stage == kABStages) { stage = 0; phase ^= 1; }
+                if (lane == 0) mbar_arrive(&a_full[stage]);
+                if (++stage == kAStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp >= 4) {
         // ================================================================= epilogue
         const int q = warp & 3;
         const uint32_t stg = smem_u32(epi_base) + static_cast<uint32_t>(q * kEpiBufBytes);
+        const int live = prm.valid_rows - q * 32;       // rows of this warp's lane quad that exist (<= 0: none)
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-            const int m_tile = t / n_tiles, n_blk = t - m_tile * n_tiles;
-            const int p = m_tile / prm.tiles_per_patch;
-            const int oh0 = (m_tile - p * prm.tiles_per_patch) * prm.TRt;
-            const int row0 = (p * Ho + oh0) * Wo + q * 32;               // < 2^31: checked by the launcher
+        for (int ps = blockIdx.x; ps < num_pass; ps += gridDim.x) {
+            const int m_tile = ps / n_groups, n0 = (ps - m_tile * n_groups) * NACC;
+            int row0;                                    // < 2^31: checked by the launcher
+            if (prm.PT == 1) {
+                const int p = m_tile / prm.tiles_per_patch;
+                row0 = (p * Ho + (m_tile - p * prm.tiles_per_patch) * prm.TRt) * Wo + q * 32;
+            } else {
+                row0 = m_tile * prm.PT * Ho * Wo + q * 32;
+            }
             mbar_wait_sleepy(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            const int n0 = n_blk * BN;
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
-            if (q * 32 < valid_rows) {                                   // valid_rows is a multiple of 32
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * NACC);
+            if (live > 0) {
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                for (int c0 = 0; c0 < NACC; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), r);
+                    const float* bp = biasp.v + n0 + c0;
                     if (lane == 0) tma_store_wait_read<0>();          // previous block's store has read the buffer
                     __syncwarp();
                     tmem_ld_wait();
-                    const float* bp = biasp.v + n0 + c0;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float4 o;
@@ -343,14 +427,19 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_2d(&map_c, stg, n0 + c0, row0);
+                        if (live >= 32) {
+                            tma_store_2d(&map_c, stg, n0 + c0, row0);
+                        } else {                                     // partial quad: whole 8-row groups only
+                            for (int r8 = 0; r8 + 8 <= live; r8 += 8)
+                                tma_store_2d(&map_c8, stg + static_cast<uint32_t>(r8 * 128), n0 + c0, row0 + r8);
+                        }
                         tma_store_commit();
                     }
                 }
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
         if (lane == 0) tma_store_wait_all();
     }
@@ -359,18 +448,20 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+        tmem_dealloc<kTmemCols>(tmem_base);
     }
 }
 
-bool encode_4d_f32(CUtensorMap* map, const float* ptr, int C, int W, int H, int P, int box_c, int box_w, int box_h) {
+bool encode_4d_f32(CUtensorMap* map, const float* ptr, int C, int W, int H, int P, int box_c, int box_w, int box_h,
+                   int box_p) {
     TensorMapEncodeFn fn = tensor_map_encode_fn();
     if (fn == nullptr) return false;
     cuuint64_t gdim[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
                           static_cast<cuuint64_t>(P)};
     cuuint64_t gstride[3] = {static_cast<cuuint64_t>(C) * 4, static_cast<cuuint64_t>(W) * C * 4,
                              static_cast<cuuint64_t>(H) * W * C * 4};
-    cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h),
+                         static_cast<cuuint32_t>(box_p)};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -378,100 +469,151 @@ bool encode_4d_f32(CUtensorMap* map, const float* ptr, int C, int W, int H, int 
     return r == CUDA_SUCCESS;
 }
 
-template <int BN, int NSPLIT, int STRIDE, int R>
-cudaError_t launch_f3_t(const CUtensorMap& map_in, const CUtensorMap& map_c, const BiasParam& bp, const PwGemmPlan& p,
-                        const F3Params& prm, int smem_bytes, int grid, cudaStream_t stream) {
-    sep_fused3_kernel<BN, NSPLIT, STRIDE, R><<<grid, kF3Threads, smem_bytes, stream>>>(map_in, p.b_hi, p.b_lo, map_c, bp, prm);
+template <int NSPLIT, int STRIDE, int NACC, bool NOHALO>
+cudaError_t launch_f3_t(const CUtensorMap& map_in, const CUtensorMap& map_c, const CUtensorMap& map_c8, const BiasParam& bp,
+                        const PwGemmPlan& p, const F3Params& prm, int smem_bytes, int grid, cudaStream_t stream) {
+    sep_fused3_kernel<NSPLIT, STRIDE, NACC, NOHALO><<<grid, kF3Threads, smem_bytes, stream>>>(map_in, p.b64_hi, p.b64_lo,
+                                                                                              map_c, map_c8, bp, prm);
     return cudaGetLastError();
 }
 
-template <int BN, int NSPLIT>
+template <int NSPLIT, int STRIDE>
 cudaError_t set_attr_f3() {
     cudaError_t e;
-#define BD_F3_ATTR(S, RR)                                                                                  \
-    if ((e = cudaFuncSetAttribute(sep_fused3_kernel<BN, NSPLIT, S, RR>,                                    \
+#define BD_F3_ATTR(NACC, NH)                                                                               \
+    if ((e = cudaFuncSetAttribute(sep_fused3_kernel<NSPLIT, STRIDE, NACC, NH>,                             \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax)) != cudaSuccess)  \
         return e;
-    BD_F3_ATTR(1, 4) BD_F3_ATTR(1, 2) BD_F3_ATTR(2, 4) BD_F3_ATTR(2, 2)
+    BD_F3_ATTR(128, false) BD_F3_ATTR(256, false) BD_F3_ATTR(512, false) BD_F3_ATTR(512, true)
 #undef BD_F3_ATTR
     return cudaSuccess;
+}
+
+// tiling of one layer: fills the geometry fields of F3Params; false if the layer does not fit this kernel
+bool plan_geometry(int K, int N, int H, int W, int stride, int box_limit, F3Params* out) {
+    if (K % kBK != 0 || N % 128 != 0 || N > kMaxN) return false;
+    if (stride != 1 && stride != 2) return false;
+    if ((H % stride) || (W % stride)) return false;
+    const int Ho = H / stride, Wo = W / stride;
+    const int bwc = stride == 1 ? 4 : 2;
+    if (Wo < bwc || (Wo & (Wo - 1)) || Wo > kBM || (Ho & 1)) return false;
+    F3Params g{};
+    g.K = K; g.N = N; g.Ho = Ho; g.Wo = Wo;
+    g.BW = (Wo - 1) * stride + 3;
+    const int px = Ho * Wo;
+    g.H = H; g.W = W;
+    if (px >= 96) {
+        // one patch per tile, TRt rows at a time; input boxes of TR rows with a one-pixel padding ring: the largest
+        // even divisor of TRt whose box stays under `box_limit` (small enough for a 4-deep ring: two stencil groups,
+        // each with a box in use and one in flight)
+        g.PT = 1; g.PB = 1; g.nohalo = 0;
+        g.TRt = Ho < kBM / Wo ? Ho : kBM / Wo;
+        if (g.TRt < 2 || Ho % g.TRt || (g.TRt & 1)) return false;
+        g.tiles_per_patch = Ho / g.TRt;
+        int tr = g.TRt;
+        while (tr > 2 && (kCB * g.BW * ((tr - 1) * stride + 3) * 4 > box_limit || g.TRt % tr || (tr & 1))) --tr;
+        if (g.TRt % tr || (tr & 1)) return false;
+        g.TR = tr;
+        g.parts = g.TRt / tr;
+        g.rows_per_part = tr * Wo;
+        g.valid_rows = g.TRt * Wo;
+        g.BH = (g.TR - 1) * stride + 3;
+    } else {
+        // small patches: PT whole patches per tile, boxes of PB whole patches WITHOUT the padding ring (a 6x4 patch
+        // with its ring would be twice the bytes); the stencil masks the taps that fall outside the patch
+        g.PT = kBM / px; g.nohalo = 1;
+        g.TRt = Ho; g.TR = Ho;
+        g.tiles_per_patch = 1;
+        g.BW = W;
+        g.BH = H;
+        const int per_patch = kCB * W * H * 4;
+        int pb = g.PT;
+        while (pb > 1 && (pb * per_patch > box_limit || g.PT % pb)) --pb;
+        g.PB = pb;
+        g.parts = g.PT / pb;
+        g.rows_per_part = pb * px;
+        g.valid_rows = g.PT * px;
+    }
+    g.blocks_w = Wo / bwc;
+    g.blocks_h = g.TR / 2;
+    g.items = g.PB * g.blocks_h * g.blocks_w * 8;
+    if (g.items > 2 * kGroupThreads || g.valid_rows % 8) return false;
+    if (kCB * g.BW * g.BH * g.PB * 4 > 64 * 1024) return false;
+    *out = g;
+    return true;
 }
 
 }  // namespace
 
 cudaError_t sep_fused3_init_device() {
     cudaError_t e;
-    if ((e = set_attr_f3<64, 1>()) != cudaSuccess) return e;
-    if ((e = set_attr_f3<128, 1>()) != cudaSuccess) return e;
-    if ((e = set_attr_f3<64, 3>()) != cudaSuccess) return e;
-    return set_attr_f3<128, 3>();
+    if ((e = set_attr_f3<1, 1>()) != cudaSuccess) return e;
+    if ((e = set_attr_f3<1, 2>()) != cudaSuccess) return e;
+    if ((e = set_attr_f3<3, 1>()) != cudaSuccess) return e;
+    return set_attr_f3<3, 2>();
 }
 
 bool sep_fused3_supported(int K, int N, int H, int W, int stride) {
-    if (K % kBK != 0 || N % 64 != 0 || N > kMaxN) return false;
-    if (stride != 1 && stride != 2) return false;
-    if ((H % stride) || (W % stride)) return false;
-    const int Ho = H / stride, Wo = W / stride;
-    if (Wo < 4 || (Wo & (Wo - 1)) || Wo > kBM) return false;
-    const int trt = Ho < kBM / Wo ? Ho : kBM / Wo;
-    if (trt < 1 || Ho % trt || (trt * Wo) % 32) return false;       // epilogue stores whole 32-row blocks
-    return true;
+    F3Params g;
+    return plan_geometry(K, N, H, W, stride, 40 * 1024, &g);
 }
 
 cudaError_t launch_sep_fused3(const PwGemmPlan& p, const float* X, const float* dw_w, const float* dw_b,
                               const float* bias_host, float* C, int P, int H, int W, int stride, int num_sms,
                               cudaStream_t stream) {
     if (P <= 0) return cudaSuccess;
-    if (!sep_fused3_supported(p.K, p.N, H, W, stride) || bias_host == nullptr) return cudaErrorInvalidValue;
-    if (p.block_n != 64 && p.block_n != 128) return cudaErrorInvalidValue;
-    const int Ho = H / stride, Wo = W / stride;
-    F3Params prm;
-    prm.dw_w = dw_w; prm.dw_b = dw_b;
-    prm.P = P; prm.K = p.K; prm.N = p.N; prm.Ho = Ho; prm.Wo = Wo;
-    prm.TRt = Ho < kBM / Wo ? Ho : kBM / Wo;
-    prm.tiles_per_patch = Ho / prm.TRt;
-    prm.BW = (Wo - 1) * stride + 3;
-    // rows per input box: the largest divisor of TRt whose box stays under ~40 KB
-    int tr = prm.TRt;
-    while (tr > 1 && (kCB * prm.BW * ((tr - 1) * stride + 3) * 4 > 40 * 1024 || prm.TRt % tr)) --tr;
-    prm.TR = tr;
-    prm.BH = (tr - 1) * stride + 3;
-    const int box_bytes = kCB * prm.BW * prm.BH * 4;
-    prm.in_stride = (box_bytes + 127) & ~127;
-    prm.out_scale = p.out_scale;
+    if (bias_host == nullptr || p.N % 128 != 0) return cudaErrorInvalidValue;
+    const int nacc = p.N >= 512 ? 512 : p.N;             // 128, 256 or 512 accumulator columns per pass
+    if (nacc != 128 && nacc != 256 && nacc != 512) return cudaErrorInvalidValue;
     const int planes = p.nsplit == 1 ? 1 : 2;
-    const int stage_bytes = planes * (kBM * kBK * 2 + p.block_n * kBK * 2);
-    const int fixed = 1024 + kABStages * stage_bytes + kEpiBytes + kBarBytes;
-    int in_stages = (kSmemMax - fixed) / prm.in_stride;
+    const int fixed = 1024 + kAStages * planes * kATile + kEpiBytes + kBarBytes;
+    const int b_slot_bytes = planes * kBSlotPlane;
+    // weight ring: enough 16 KB slots in flight to cover the L2 round trip at the MMA's consumption rate (the wider
+    // the accumulator, the more slots one k-block eats); the rest of shared memory is the input ring
+    // Measured (profiles/r1_summary.md): fewer, larger boxes beat a deeper ring of small ones (per-box barrier and
+    // tap-weight reload cost), and shared memory left to L1 matters because the tap weights are re-read per box.
+    int b_slots = nacc == 128 ? 4 : 5;
+    const int ring_bytes = kSmemMax - fixed - b_slots * b_slot_bytes;
+    F3Params prm;
+    if (!plan_geometry(p.K, p.N, H, W, stride, 40 * 1024, &prm)) return cudaErrorInvalidValue;
+    prm.dw_w = dw_w; prm.dw_b = dw_b;
+    prm.P = P;
+    prm.out_scale = p.out_scale;
+    prm.m_tiles = prm.PT == 1 ? P * prm.tiles_per_patch : (P + prm.PT - 1) / prm.PT;
+    const int box_bytes = kCB * prm.BW * prm.BH * prm.PB * 4;
+    prm.in_stride = (box_bytes + 127) & ~127;
+    int in_stages = ring_bytes / prm.in_stride;
     if (in_stages > kMaxInStages) in_stages = kMaxInStages;
     if (in_stages < 2) return cudaErrorInvalidValue;
+    prm.b_slots = b_slots;
     prm.in_stages = in_stages;
-    const int smem_bytes = fixed + in_stages * prm.in_stride;
-    // strip length: 4 output pixels when that still gives most stencil threads a strip, else 2
-    const int items4 = (kCB / 4) * (prm.TR * Wo / 4);
-    const int R = (Wo % 4 == 0 && items4 >= 192) ? 4 : 2;
-    const long long tiles = static_cast<long long>(P) * prm.tiles_per_patch * (p.N / p.block_n);
-    if (tiles >= (1LL << 31)) return cudaErrorInvalidValue;
-    const int grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
-    CUtensorMap map_in, map_c;
-    if (!encode_4d_f32(&map_in, X, p.K, W, H, P, kCB, prm.BW, prm.BH)) return cudaErrorUnknown;
-    const long long m_rows = static_cast<long long>(P) * Ho * Wo;
-    if (m_rows >= (1LL << 31) || !encode_store_map_f32(&map_c, C, m_rows, p.N)) return cudaErrorUnknown;
+    const int smem_bytes = fixed + b_slots * b_slot_bytes + in_stages * prm.in_stride;
+    const long long passes = static_cast<long long>(prm.m_tiles) * (p.N / nacc);
+    const long long m_rows = static_cast<long long>(P) * prm.Ho * prm.Wo;
+    if (passes >= (1LL << 31) || m_rows + kBM >= (1LL << 31)) return cudaErrorInvalidValue;
+    const int grid = static_cast<int>(passes < num_sms ? passes : num_sms);
+    CUtensorMap map_in, map_c, map_c8;
+    if (!encode_4d_f32(&map_in, X, p.K, W, H, P, kCB, prm.BW, prm.BH, prm.PB)) return cudaErrorUnknown;   // box <= tensor in nohalo mode
+    if (!encode_store_map_f32(&map_c, C, m_rows, p.N, 32) || !encode_store_map_f32(&map_c8, C, m_rows, p.N, 8))
+        return cudaErrorUnknown;
     BiasParam bp;
     for (int i = 0; i < kMaxN; ++i) bp.v[i] = i < p.N ? bias_host[i] : 0.f;
-#define BD_F3(BN, NS)                                                                                              \
-    do {                                                                                                           \
-        if (stride == 1) return R == 4 ? launch_f3_t<BN, NS, 1, 4>(map_in, map_c, bp, p, prm, smem_bytes, grid, stream)       \
-                                       : launch_f3_t<BN, NS, 1, 2>(map_in, map_c, bp, p, prm, smem_bytes, grid, stream);      \
-        return R == 4 ? launch_f3_t<BN, NS, 2, 4>(map_in, map_c, bp, p, prm, smem_bytes, grid, stream)                        \
-                      : launch_f3_t<BN, NS, 2, 2>(map_in, map_c, bp, p, prm, smem_bytes, grid, stream);                       \
+#define BD_F3(NS, S)                                                                                             \
+    do {                                                                                                         \
+        if (prm.nohalo) {                                                                                        \
+            if (nacc != 512) return cudaErrorInvalidValue;                                                       \
+            return launch_f3_t<NS, S, 512, true>(map_in, map_c, map_c8, bp, p, prm, smem_bytes, grid, stream);    \
+        }                                                                                                        \
+        if (nacc == 128) return launch_f3_t<NS, S, 128, false>(map_in, map_c, map_c8, bp, p, prm, smem_bytes, grid, stream); \
+        if (nacc == 256) return launch_f3_t<NS, S, 256, false>(map_in, map_c, map_c8, bp, p, prm, smem_bytes, grid, stream); \
+        return launch_f3_t<NS, S, 512, false>(map_in, map_c, map_c8, bp, p, prm, smem_bytes, grid, stream);      \
     } while (0)
     if (p.nsplit == 1) {
-        if (p.block_n == 64) BD_F3(64, 1);
-        BD_F3(128, 1);
+        if (stride == 1) BD_F3(1, 1);
+        BD_F3(1, 2);
     }
-    if (p.block_n == 64) BD_F3(64, 3);
-    BD_F3(128, 3);
+    if (stride == 1) BD_F3(3, 1);
+    BD_F3(3, 2);
 #undef BD_F3
 }
 
