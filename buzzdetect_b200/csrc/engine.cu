@@ -497,9 +497,10 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
     // which separable blocks run fused: bit (L-2) for layer L.  Measured on B200 (profiles/fusion_r1.md): with the
     // current register-fed producers only layer 3 (stride 2, K=64) beats the two-kernel path, so that is the default.
     // Default (fuse_mask < 0), measured on B200 (profiles/r1_summary.md): layers 1+2 in the warp-specialised
-    // l12_fused2_kernel, layers 3..6 in sep_fused3_kernel (TMA-staged stencil input); layer 7 and the 6x4 / 3x2 layers
-    // stay as depthwise + GEMM pairs (their output tiles would straddle patches).
-    const int cfg_mask = cfg->fuse_mask < 0 ? (BD_FUSE_L12V2 | BD_FUSE_V3 | BD_FUSE_CONV1_DW2 | 0x1E) : cfg->fuse_mask;
+    // l12_fused2_kernel, layers 3..6 and 8..12 in sep_fused3_kernel (TMA-staged stencil input, whole-patch tiles for
+    // the 6x4 layers); layer 7 (stride 2 into 6x4: five small boxes per tile) and the 3x2 layers 13-14 stay as
+    // depthwise + GEMM pairs.
+    const int cfg_mask = cfg->fuse_mask < 0 ? (BD_FUSE_L12V2 | BD_FUSE_V3 | BD_FUSE_CONV1_DW2 | 0x7DE) : cfg->fuse_mask;
     const int fuse_mask = e->precision == BD_PRECISION_FP32_SIMT ? 0 : (cfg_mask & 0x1FFF);
     const bool use_v3 = (cfg_mask & BD_FUSE_V3) != 0;
     e->fuse_conv1 = (cfg_mask & BD_FUSE_CONV1_DW2) != 0;

@@ -6,6 +6,8 @@
 // TensorFlow SAME padding: stride 1 pads (1,1); stride 2 on even sizes pads (0 before, 1 after) -- SURVEY.md 2a.
 // BatchNorm is folded into weights/bias on the host (buzzdetect_b200/weights.py:fold_yamnet).
 // Layout: NHWC, H = time, W = mel; activations are [P*H*W, C] row-major so a pointwise conv is a plain GEMM.
+#include <cstdlib>
+
 #include "bd_kernels.cuh"
 
 namespace bd {
@@ -268,6 +270,100 @@ __global__ void __launch_bounds__(256) depthwise_kernel(const float* __restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------ depthwise, 2-row blocks
+// Same op, thread = (block of R x 2 output pixels, 4 channels): the (2*STRIDE+1 | 4) x NC input window is walked row by
+// row, every row feeding both output rows, so an output vector costs 3 (stride 1) instead of 4.5 global loads and the
+// nine tap vectors are fetched once per 2R instead of once per R pixels.  Used when the output height is even; the
+// L1/texture data pipe (one 128-byte wavefront per clock per SM), not HBM, is what bounds these kernels.
+template <int STRIDE, int R, int OUT_MODE>
+__global__ void __launch_bounds__(256) depthwise2_kernel(const float* __restrict__ in, int P, int H, int W, int C,
+                                                         const float* __restrict__ w, const float* __restrict__ b,
+                                                         float* __restrict__ out_f32, __half* __restrict__ out_hi,
+                                                         __half* __restrict__ out_lo) {
+    const int Ho = H / STRIDE, Wo = W / STRIDE;
+    constexpr int PB = STRIDE == 1 ? 1 : 0;
+    constexpr int NC = (R - 1) * STRIDE + 3;
+    constexpr int NR = STRIDE + 3;                                                  // input rows per block
+    const unsigned c4_bits = 31u - __clz(static_cast<unsigned>(C >> 2));
+    const unsigned ws_bits = 31u - __clz(static_cast<unsigned>(Wo / R));
+    const unsigned items = static_cast<unsigned>(Ho >> 1) << (ws_bits + c4_bits);  // per patch
+    const unsigned bpp = (items + blockDim.x - 1) / blockDim.x;
+    for (unsigned bid = blockIdx.x; bid < static_cast<unsigned>(P) * bpp; bid += gridDim.x) {
+        const unsigned pi = bid / bpp;
+        const unsigned item = (bid - pi * bpp) * blockDim.x + threadIdx.x;
+        if (item >= items) continue;
+        const int c4 = static_cast<int>(item & ((1u << c4_bits) - 1u));
+        const int ws = static_cast<int>((item >> c4_bits) & ((1u << ws_bits) - 1u));
+        const int oh0 = static_cast<int>(item >> (c4_bits + ws_bits)) * 2;
+        const long long p = pi;
+        const int ow0 = ws * R;
+        const float* inp = in + p * H * W * C + c4 * 4;
+        float4 k[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) k[i] = __ldg(reinterpret_cast<const float4*>(w + i * C + c4 * 4));
+        const float4 bias = __ldg(reinterpret_cast<const float4*>(b + c4 * 4));
+        float4 acc[2][R];
+#pragma unroll
+        for (int o = 0; o < 2; ++o)
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[o][r] = bias;
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            const int ih = oh0 * STRIDE + i - PB;
+            if (ih < 0 || ih >= H) continue;
+            const float* rowp = inp + static_cast<long long>(ih) * W * C;
+            float4 v[NC];
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+                const int iw = ow0 * STRIDE - PB + j;
+                v[j] = (iw >= 0 && iw < W) ? __ldg(reinterpret_cast<const float4*>(rowp + static_cast<long long>(iw) * C))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+                const int kh = i - o * STRIDE;
+                if (kh < 0 || kh > 2) continue;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const float4 x = v[r * STRIDE + kw];
+                        const float4 kk = k[kh * 3 + kw];
+                        acc[o][r].x = fmaf(x.x, kk.x, acc[o][r].x);
+                        acc[o][r].y = fmaf(x.y, kk.y, acc[o][r].y);
+                        acc[o][r].z = fmaf(x.z, kk.z, acc[o][r].z);
+                        acc[o][r].w = fmaf(x.w, kk.w, acc[o][r].w);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+            const long long pix0 = (p * Ho + oh0 + o) * Wo + ow0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float4 a = acc[o][r];
+                a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+                const long long oo = (pix0 + r) * C + c4 * 4;
+                if (OUT_MODE == 0) {
+                    *reinterpret_cast<float4*>(out_f32 + oo) = a;
+                } else {
+                    const __half h0 = __float2half_rn(a.x), h1 = __float2half_rn(a.y);
+                    const __half h2 = __float2half_rn(a.z), h3 = __float2half_rn(a.w);
+                    __half2 hp[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
+                    *reinterpret_cast<uint2*>(out_hi + oo) = *reinterpret_cast<uint2*>(hp);
+                    if (OUT_MODE == 2) {
+                        __half2 lp[2] = {
+                            __halves2half2(__float2half_rn(a.x - __half2float(h0)), __float2half_rn(a.y - __half2float(h1))),
+                            __halves2half2(__float2half_rn(a.z - __half2float(h2)), __float2half_rn(a.w - __half2float(h3)))};
+                        *reinterpret_cast<uint2*>(out_lo + oo) = *reinterpret_cast<uint2*>(lp);
+                    }
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ SIMT fp32 GEMM
 // C[M,N] = relu(A[M,K] * Bt[N,K]^T + bias[N]); 64x64 tile, 16-wide K slabs, 4x4 outputs per thread.
 __global__ void __launch_bounds__(256) pw_simt_kernel(const float* __restrict__ A, const float* __restrict__ Bt,
@@ -348,6 +444,13 @@ __global__ void __launch_bounds__(256) pool_head_kernel(const float* __restrict_
     }
 }
 
+// experiment switch: BD_DW_TWO_ROWS=1 selects the two-row blocks.  Measured on B200: 102 registers cost a resident CTA
+// per SM and the 6x4 layers get SLOWER (0.094 -> 0.119 ms per audio-hour), so one-row strips stay the default.
+inline bool dw_two_rows_enabled() {
+    static const int v = [] { const char* e = getenv("BD_DW_TWO_ROWS"); return e ? atoi(e) : 0; }();
+    return v != 0;
+}
+
 inline int grid_for(long long total, int block, int cap) {
     long long g = (total + block - 1) / block;
     if (g > cap) g = cap;
@@ -400,10 +503,26 @@ cudaError_t launch_depthwise(const float* in, int P, int H, int W, int C, int st
     const int R = (Wo % 4 == 0) ? 4 : ((Wo % 2 == 0) ? 2 : 1);
     const unsigned c4 = static_cast<unsigned>(C / 4), wsn = static_cast<unsigned>(Wo / R);
     if ((c4 & (c4 - 1)) || (wsn & (wsn - 1))) return cudaErrorInvalidValue;      // shift/mask indexing (see kernel)
-    const long long items = static_cast<long long>(H / stride) * wsn * c4;
+    const bool two_rows = ((H / stride) % 2 == 0) && (R == 4 || R == 2) && dw_two_rows_enabled();
+    const long long items = static_cast<long long>(H / stride) / (two_rows ? 2 : 1) * wsn * c4;
     const long long blocks = static_cast<long long>(P) * ((items + 255) / 256);
     if (blocks >= (1LL << 31)) return cudaErrorInvalidValue;
     const int grid = static_cast<int>(blocks < 148LL * 64 ? blocks : 148LL * 64);
+    if (two_rows) {
+#define BD_DW2(S, RR, MODE) \
+    depthwise2_kernel<S, RR, MODE><<<grid, 256, 0, stream>>>(in, P, H, W, C, w, b, out_f32, out_hi, out_lo)
+#define BD_DW2_MODE(S, RR)                          \
+    do {                                            \
+        if (out_mode == 0) BD_DW2(S, RR, 0);        \
+        else if (out_mode == 1) BD_DW2(S, RR, 1);   \
+        else BD_DW2(S, RR, 2);                      \
+    } while (0)
+        if (stride == 1) { if (R == 4) BD_DW2_MODE(1, 4); else BD_DW2_MODE(1, 2); }
+        else { if (R == 4) BD_DW2_MODE(2, 4); else BD_DW2_MODE(2, 2); }
+#undef BD_DW2_MODE
+#undef BD_DW2
+        return cudaGetLastError();
+    }
 #define BD_DW(S, RR, MODE) \
     depthwise_kernel<S, RR, MODE><<<grid, 256, 0, stream>>>(in, P, H, W, C, w, b, out_f32, out_hi, out_lo)
 #define BD_DW_MODE(S, RR)                          \

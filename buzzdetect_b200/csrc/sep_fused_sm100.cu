@@ -12,9 +12,11 @@
 //   warps 8-15  stencil: two groups of four warps take alternate boxes; a thread owns 4 channels of a 4x2 (stride 1)
 //               or 2x2 (stride 2) block of output pixels (3 / 6.25 LDS.128 per output vector), and writes hi/lo fp16
 //               straight into the SWIZZLE_128B K-major A tile (2 stages of 128 rows x 64 channels).
-//   warp 0      weight TMA: 64-row x 64-channel boxes of the hi/lo weight planes into a ring of 16 KB slots.
-//   warp 1      tcgen05.mma issuer: per k-block, NACC/64 weight slots x 4 k-steps x (1 | 3) MMAs (M=128, N=64, K=16)
-//               into TMEM columns [slot*64, +64) -- the A tile is read NACC/64 times, the stencil computed once.
+//   warp 0      weight TMA: 128-row x 64-channel boxes of the hi/lo weight planes into a ring of 32 KB slots.
+//   warp 1      tcgen05.mma issuer: per k-block, NACC/128 weight slots x 4 k-steps x (1 | 3) MMAs (M=128, N=128, K=16)
+//               into TMEM columns [slot*128, +128) -- the A tile is read NACC/128 times, the stencil computed once.
+//               (An MMA costs about (4 KB of A + 32 B x N of B) / 64 B per clock of shared-memory operand fetch, more
+//               than its math below N = 256: N = 64 slots ran the tensor pipe at a third of its rate.)
 //   warp 2      TMEM allocator: NACC <= 256: two accumulator stages; NACC = 512: one stage = all 512 columns.
 //   warps 4-7   epilogue: tcgen05.ld -> scale + bias (constant bank) + ReLU -> swizzled smem block -> TMA store.
 //
@@ -24,6 +26,8 @@
 // Why these choices (measured, profiles/r1_summary.md): the kernels of this family are bound by the SM's L1/shared
 // data pipe (one 128-byte wavefront per clock), not by HBM or FMA issue -- hence block-shaped stencils, bias from the
 // constant bank, and TMA stores instead of LDS + STG in the epilogue.
+#include <cstdlib>
+
 #include "bd_common.cuh"
 #include "bd_kernels.cuh"
 
@@ -34,7 +38,7 @@ namespace {
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kCB = 32;                                          // channels per input box (128-byte pixel rows)
-constexpr int kBNs = 64;                                         // weight rows per ring slot = MMA N
+constexpr int kBNs = 128;                                        // weight rows per ring slot = MMA N
 constexpr int kF3Threads = 512;
 constexpr int kGroupThreads = 128;                               // stencil group = 4 warps
 constexpr int kEpiBufBytes = 32 * 128;                           // one [32 rows x 32 float] swizzled block per epilogue warp
@@ -46,7 +50,7 @@ constexpr int kSmemMax = 227 * 1024;
 constexpr int kBarBytes = 320;
 constexpr int kMaxN = 512;
 constexpr int kATile = kBM * kBK * 2;                            // one fp16 plane of the A tile, 16 KB
-constexpr int kBSlotPlane = kBNs * kBK * 2;                      // 8 KB
+constexpr int kBSlotPlane = kBNs * kBK * 2;                      // 16 KB
 
 struct BiasParam { float v[kMaxN]; };                            // kernel parameter = constant bank (no L1 traffic)
 
@@ -65,6 +69,7 @@ struct F3Params {
     int m_tiles;
     int in_stages, in_stride;   // input ring depth, bytes between slots
     int b_slots;
+    int prefetch_boxes;      // how far the L2 prefetch cursor runs ahead of the loads (0 = off)
     int nohalo;              // 1: boxes hold whole patches without the padding ring; the stencil masks its border taps
     int H, W;                // input extent per patch
     int items;               // stencil blocks per box (x 8 channel quads)
@@ -79,6 +84,13 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* map, uin
         ::"r"(smem_u32(smem_dst)),
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
+}
+
+__device__ __forceinline__ void tma_prefetch_4d(const void* map, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
 }
 
 // hi/lo fp16 of 4 channels of one pixel -> the swizzled A tile (row = pixel, 128-byte rows, 16-byte chunks XOR row&7)
@@ -210,37 +222,65 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
         // ================================================================= input TMA (float32 NHWC boxes)
         if (lane == 0) {
             const uint32_t box_bytes = static_cast<uint32_t>(kCB * prm.BW * prm.BH * prm.PB * 4);
-            int is = 0;
-            uint32_t iphase = 0;
-            for (int ps = blockIdx.x; ps < num_pass; ps += gridDim.x) {
-                const int m_tile = ps / n_groups;
-                int p0, oh0;
-                if (prm.PT == 1) {
-                    p0 = m_tile / prm.tiles_per_patch;
-                    oh0 = (m_tile - p0 * prm.tiles_per_patch) * prm.TRt;
-                } else {
-                    p0 = m_tile * prm.PT;
-                    oh0 = 0;
-                }
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    for (int sb = 0; sb < kBK / kCB; ++sb) {
-                        for (int part = 0; part < parts; ++part) {
-                            const int oh = prm.PT == 1 ? oh0 + part * prm.TR : 0;
-                            const int pp = prm.PT == 1 ? p0 : p0 + part * prm.PB;
-                            mbar_wait(&in_empty[is], iphase ^ 1);
-                            mbar_arrive_expect_tx(&in_full[is], box_bytes);
-                            tma_load_4d(in_ring + is * prm.in_stride, &map_in, &in_full[is], kb * kBK + sb * kCB,
-                                        (STRIDE == 1 && !NOHALO) ? -1 : 0,
-                                        NOHALO ? 0 : (STRIDE == 1 ? oh - 1 : 2 * oh), pp);
-                            if (++is == in_stages) { is = 0; iphase ^= 1; }
-                        }
+            // Two cursors over the same box sequence: `pf` runs kPrefetchBoxes ahead and only asks L2 for the box
+            // (cp.async.bulk.prefetch.tensor), `cur` issues the real loads.  The ring holds 2-4 boxes (shared memory is
+            // spent on the GEMM operands), which covers an L2 hit but not a DRAM round trip; with the prefetch the ring
+            // only ever waits on L2.
+            struct Cursor { int ps, kb, sb, part; };
+            auto advance = [&](Cursor& c) {
+                if (++c.part == parts) {
+                    c.part = 0;
+                    if (++c.sb == kBK / kCB) {
+                        c.sb = 0;
+                        if (++c.kb == num_kb) { c.kb = 0; c.ps += gridDim.x; }
                     }
                 }
+            };
+            auto coords = [&](const Cursor& c, int& c0, int& cw, int& ch, int& cp) {
+                const int m_tile = c.ps / n_groups;
+                int p0, oh;
+                if (prm.PT == 1) {
+                    p0 = m_tile / prm.tiles_per_patch;
+                    oh = (m_tile - p0 * prm.tiles_per_patch) * prm.TRt + c.part * prm.TR;
+                } else {
+                    p0 = m_tile * prm.PT + c.part * prm.PB;
+                    oh = 0;
+                }
+                c0 = c.kb * kBK + c.sb * kCB;
+                cw = (STRIDE == 1 && !NOHALO) ? -1 : 0;
+                ch = NOHALO ? 0 : (STRIDE == 1 ? oh - 1 : 2 * oh);
+                cp = p0;
+            };
+            Cursor cur{static_cast<int>(blockIdx.x), 0, 0, 0}, pf = cur;
+            int c0, cw, ch, cp;
+            for (int i = 0; i < prm.prefetch_boxes && pf.ps < num_pass; ++i) {
+                coords(pf, c0, cw, ch, cp);
+                tma_prefetch_4d(&map_in, c0, cw, ch, cp);
+                advance(pf);
+            }
+            int is = 0;
+            uint32_t iphase = 0;
+            while (cur.ps < num_pass) {
+                if (pf.ps < num_pass && prm.prefetch_boxes > 0) {
+                    coords(pf, c0, cw, ch, cp);
+                    tma_prefetch_4d(&map_in, c0, cw, ch, cp);
+                    advance(pf);
+                }
+                coords(cur, c0, cw, ch, cp);
+                mbar_wait(&in_empty[is], iphase ^ 1);
+                mbar_arrive_expect_tx(&in_full[is], box_bytes);
+                tma_load_4d(in_ring + is * prm.in_stride, &map_in, &in_full[is], c0, cw, ch, cp);
+                if (++is == in_stages) { is = 0; iphase ^= 1; }
+                advance(cur);
             }
         }
     } else if (warp == 1) {
         // ================================================================= MMA issuer
-        if (lane == 0) {
+        // The WHOLE warp walks the loops and waits on the barriers; only the tcgen05 instructions sit under elect_one().
+        // With the loop inside `if (lane == 0)` every address and descriptor lives in per-thread registers and each
+        // MMA drags a chain of R2UR moves behind it (~120 clk per issue, measured): with 32-clock N=64 MMAs the
+        // tensor pipe then idles three quarters of the time.  Warp-uniform control flow keeps them in uniform registers.
+        {
             constexpr uint32_t idesc = umma_idesc_f16(kBM, kBNs);
             int stage = 0, bs = 0, acc = 0;
             uint32_t phase = 0, bphase = 0, acc_phase = 0;
@@ -252,34 +292,35 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
                     mbar_wait(&a_full[stage], phase);
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(a_base + stage * kAStageBytes);
-                    const uint32_t a_lo = a_hi + kATile;
+                    const uint64_t da_hi = umma_desc_k128(a_hi), da_lo = umma_desc_k128(a_hi + kATile);
 #pragma unroll 1
                     for (int nb = 0; nb < kSlotsPerKb; ++nb) {
                         mbar_wait(&b_full[bs], bphase);
                         tc_fence_after();
                         const uint32_t b_hi = smem_u32(b_base + bs * kBSlotBytes);
-                        const uint32_t b_lo = b_hi + kBSlotPlane;
+                        const uint64_t db_hi = umma_desc_k128(b_hi), db_lo = umma_desc_k128(b_hi + kBSlotPlane);
                         const uint32_t d_tmem = d_acc + static_cast<uint32_t>(nb * kBNs);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < kBK / 16; ++k) {
-                            const uint32_t koff = static_cast<uint32_t>(k) * 32u;
-                            const uint64_t da_hi = umma_desc_k128(a_hi + koff);
-                            const uint64_t db_hi = umma_desc_k128(b_hi + koff);
-                            umma_f16_ss(d_tmem, da_hi, db_hi, idesc, (kb | k) != 0 ? 1u : 0u);
-                            if (NSPLIT > 1) {
-                                const uint64_t da_lo = umma_desc_k128(a_lo + koff);
-                                const uint64_t db_lo = umma_desc_k128(b_lo + koff);
-                                umma_f16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
-                                umma_f16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
+                            for (int k = 0; k < kBK / 16; ++k) {
+                                const uint64_t koff = static_cast<uint64_t>(k) * 2u;     // 16 fp16 = 32 bytes, >> 4
+                                umma_f16_ss(d_tmem, da_hi + koff, db_hi + koff, idesc, (kb | k) != 0 ? 1u : 0u);
+                                if (NSPLIT > 1) {
+                                    umma_f16_ss(d_tmem, da_lo + koff, db_hi + koff, idesc, 1u);
+                                    umma_f16_ss(d_tmem, da_hi + koff, db_lo + koff, idesc, 1u);
+                                }
+                            }
+                            umma_commit(&b_empty[bs]);
+                            if (nb == kSlotsPerKb - 1) {
+                                umma_commit(&a_empty[stage]);
+                                if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
                             }
                         }
-                        umma_commit(&b_empty[bs]);
+                        __syncwarp();
                         if (++bs == b_slots) { bs = 0; bphase ^= 1; }
                     }
-                    umma_commit(&a_empty[stage]);
                     if (++stage == kAStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full[acc]);
                 if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -472,7 +513,7 @@ bool encode_4d_f32(CUtensorMap* map, const float* ptr, int C, int W, int H, int 
 template <int NSPLIT, int STRIDE, int NACC, bool NOHALO>
 cudaError_t launch_f3_t(const CUtensorMap& map_in, const CUtensorMap& map_c, const CUtensorMap& map_c8, const BiasParam& bp,
                         const PwGemmPlan& p, const F3Params& prm, int smem_bytes, int grid, cudaStream_t stream) {
-    sep_fused3_kernel<NSPLIT, STRIDE, NACC, NOHALO><<<grid, kF3Threads, smem_bytes, stream>>>(map_in, p.b64_hi, p.b64_lo,
+    sep_fused3_kernel<NSPLIT, STRIDE, NACC, NOHALO><<<grid, kF3Threads, smem_bytes, stream>>>(map_in, p.b_hi, p.b_lo,
                                                                                               map_c, map_c8, bp, prm);
     return cudaGetLastError();
 }
@@ -572,7 +613,7 @@ cudaError_t launch_sep_fused3(const PwGemmPlan& p, const float* X, const float* 
     // the accumulator, the more slots one k-block eats); the rest of shared memory is the input ring
     // Measured (profiles/r1_summary.md): fewer, larger boxes beat a deeper ring of small ones (per-box barrier and
     // tap-weight reload cost), and shared memory left to L1 matters because the tap weights are re-read per box.
-    int b_slots = nacc == 128 ? 4 : 5;
+    int b_slots = nacc == 512 ? 3 : 2;
     const int ring_bytes = kSmemMax - fixed - b_slots * b_slot_bytes;
     F3Params prm;
     if (!plan_geometry(p.K, p.N, H, W, stride, 40 * 1024, &prm)) return cudaErrorInvalidValue;
@@ -587,6 +628,12 @@ cudaError_t launch_sep_fused3(const PwGemmPlan& p, const float* X, const float* 
     if (in_stages < 2) return cudaErrorInvalidValue;
     prm.b_slots = b_slots;
     prm.in_stages = in_stages;
+    {
+        // Measured on B200: asking L2 for the boxes ahead of time does not help (layers 3-6 within +-2 %, layer 3
+        // slower) -- the ring is not what these kernels wait on.  Kept as an experiment knob, off by default.
+        static const int pf_env = [] { const char* e = getenv("BD_F3_PREFETCH"); return e ? atoi(e) : 0; }();
+        prm.prefetch_boxes = pf_env;
+    }
     const int smem_bytes = fixed + b_slots * b_slot_bytes + in_stages * prm.in_stride;
     const long long passes = static_cast<long long>(prm.m_tiles) * (p.N / nacc);
     const long long m_rows = static_cast<long long>(P) * prm.Ho * prm.Wo;

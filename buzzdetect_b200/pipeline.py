@@ -9,8 +9,8 @@ restated without soundfile / librosa / pandas / TensorFlow:
   * WorkerWriter.write_results                 src/write/worker.py:67-87     (append `<ident>_buzzpart.csv`; when the
     file is complete: sort by start, write `<ident>_buzzdetect.csv`, delete the partial)
 
-Audio is read with the stdlib `wave` module (PCM16 / PCM32-float WAV only -- the reference's codec zoo is out of scope)
-and handed to the GPU in its decoded form: downmix + resample + frontend + CNN + head run in one C-ABI call per chunk
+Audio is read with the stdlib `wave` module (PCM16 WAV) or, for compressed formats such as the reference's own
+`audio_in/testbuzz.mp3`, decoded through FFmpeg via ctypes (buzzdetect_b200/audio.py), and handed to the GPU in its decoded form: downmix + resample + frontend + CNN + head run in one C-ABI call per chunk
 (`bd_submit_pcm_host`), several chunks in flight.  The coordinator / logging / manifest layers are NOT rebuilt here.
 """
 from __future__ import annotations
@@ -26,6 +26,8 @@ from . import capi, config as cfg, stream, write
 
 class WavTrack:
     """Minimal stand-in for the reference's AudioDriver (src/stream/driver.py:3-22) over RIFF/WAVE PCM16."""
+
+    fmt = 1                                     # int16 PCM for bd_submit_pcm_host
 
     def __init__(self, path: str):
         self._w = wave.open(path, "rb")
@@ -49,6 +51,45 @@ class WavTrack:
 
     def close(self):
         self._w.close()
+
+
+class DecodedTrack:
+    """Compressed formats (mp3, flac, ogg, m4a ...): decoded once on the host through FFmpeg (buzzdetect_b200.audio,
+    the reference's PyAV fallback without PyAV, src/stream/audio.py:29-44) and served from memory as float32."""
+
+    fmt = 0                                     # float32 PCM for bd_submit_pcm_host
+
+    def __init__(self, path: str):
+        from . import audio
+        self._x, self.samplerate = audio.decode_file(path)
+        self.channels = 1 if self._x.ndim == 1 else self._x.shape[1]
+        self.frames = self._x.shape[0]
+        self._pos = 0
+
+    @property
+    def duration(self) -> float:
+        return self.frames / self.samplerate
+
+    def seek(self, frame: int):
+        self._pos = min(max(frame, 0), self.frames)
+
+    def read(self, n: int) -> np.ndarray:
+        a = self._x[self._pos:self._pos + n]
+        self._pos += a.shape[0]
+        return a
+
+    def close(self):
+        self._x = None
+
+
+def open_track(path: str):
+    """WAV PCM16 through the stdlib reader, everything else through FFmpeg."""
+    if path.lower().endswith(".wav"):
+        try:
+            return WavTrack(path)
+        except (ValueError, wave.Error):
+            pass
+    return DecodedTrack(path)
 
 
 def _fmt(v) -> str:
@@ -100,7 +141,7 @@ def analyze_wav(path_audio: str, dir_out: str, engine: "capi.Engine", classes: l
     framehop_s = framelength_s * framehop_prop
     hop_frames = capi.hop_frames_for(framehop_prop)
     chunklength = stream.setup_chunklength(chunklength, framelength_s)
-    track = WavTrack(path_audio)
+    track = open_track(path_audio)
     covered = _read_partial_starts(partial) if os.path.exists(partial) else None
     chunklist = stream.file_chunklist(track.duration, chunklength, covered, framelength_s)
     if covered is not None and not chunklist:
@@ -138,8 +179,8 @@ def analyze_wav(path_audio: str, dir_out: str, engine: "capi.Engine", classes: l
                 n16 = int(engine._lib.bd_resample_out_len(n_read, track.samplerate))
                 _, _, P = capi.frames_for(n16, hop_frames)
                 act = np.empty((P, engine.n_classes), dtype=np.float32)
-                engine.submit_pcm_ptr(slot, pcm.ctypes.data, 1, track.channels, n_read, track.samplerate, hop_frames,
-                                      act.ctypes.data)
+                engine.submit_pcm_ptr(slot, pcm.ctypes.data, track.fmt, track.channels, n_read, track.samplerate,
+                                      hop_frames, act.ctypes.data)
                 pending.append((slot, chunk, act, pcm))
             if short:
                 break
@@ -159,7 +200,7 @@ def analyze_files(paths: list[str], dir_out: str, rank: int = 0, world_size: int
     from .inference.models import load_model
     durations = []
     for p in paths:
-        t = WavTrack(p)
+        t = open_track(p)
         durations.append(t.duration)
         t.close()
     chunklength = stream.setup_chunklength(kw.get("chunklength", 1198.08))

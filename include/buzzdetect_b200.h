@@ -74,7 +74,7 @@ typedef struct bd_config {
                                       (ignored in BD_PRECISION_FP32_SIMT); BD_FUSE_CONV1_DW2: layer 1 + layer-2
                                       depthwise in one kernel; BD_FUSE_L12: layers 1+2 in one kernel.
                                       BD_FUSE_V3 / BD_FUSE_L12V2: use the TMA-staged / warp-specialised variants.
-                                      -1 = default (BD_FUSE_L12V2 | BD_FUSE_V3 | BD_FUSE_CONV1_DW2 | layers 3..6).       */
+                                      -1 = default (BD_FUSE_L12V2 | BD_FUSE_V3 | BD_FUSE_CONV1_DW2 | layers 3..6, 8..12).       */
 } bd_config;
 
 int32_t bd_abi_version(void);

@@ -226,11 +226,11 @@ def test_device_resident_entry_point(engines):
     assert P == want.shape[0]
     assert np.array_equal(dact.cpu().numpy(), want)
     prof = e.profile_device_ptr(dx.data_ptr(), dx.numel(), 96)
-    # defaults: layers 1+2 run as one kernel (counted as conv1), layers 3..6 run fused with their pointwise
-    assert prof["pointwise"]["launches"] == 12 and prof["depthwise"]["launches"] == 8
+    # defaults: layers 1+2 run as one kernel (counted as conv1), layers 3..6 and 8..12 run fused with their pointwise
+    assert prof["pointwise"]["launches"] == 12 and prof["depthwise"]["launches"] == 3
     assert all(prof[k]["ms"] > 0 for k in ("frontend", "conv1", "depthwise", "pointwise", "pool_head"))
     assert [v["pw_launches"] for v in prof["layers"].values()] == [0] + [1] * 12
-    assert [v["dw_launches"] for v in prof["layers"].values()] == [0] * 5 + [1] * 8
+    assert [v["dw_launches"] for v in prof["layers"].values()] == [0] * 5 + [1] + [0] * 5 + [1, 1]
 
 
 # ------------------------------------------------------------------------------------------------ full-size properties
