@@ -165,8 +165,21 @@ def run_ours(args, rank, world, local):
     if use_dist:
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        dist.barrier()
+        # NCCL announces its version on stdout when NCCL_DEBUG asks for it; stdout carries exactly one JSON line, so
+        # anything the communicator setup prints goes to stderr instead
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            t0_ = torch.zeros(1, device="cuda")
+            dist.all_reduce(t0_)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     from buzzdetect_b200 import capi
     from oracle import yamnet_oracle as O            # synthetic audio generator + cpu_baseline only
 
@@ -219,16 +232,20 @@ def run_ours(args, rank, world, local):
         outs.append(torch.empty((p, eng.n_classes), dtype=torch.float32).pin_memory())
     n_slots = 4
 
-    def e2e_run(steps):
+    def e2e_run(steps, pcm16=None):
         """`steps` recordings back to back; chunks stay pipelined across recordings (a streamer never drains the
-        GPU between files), everything is drained before the clock stops."""
+        GPU between files), everything is drained before the clock stops.  pcm16: the same recording as int16 PCM,
+        submitted through the PCM entry point (what a WAV streamer holds: half the bytes over PCIe)."""
         j = 0
         for _ in range(steps):
             for i, (o, m) in enumerate(chunks):
                 s = j % n_slots
                 j += 1
                 eng.wait(s)
-                eng.submit_ptr(s, host.data_ptr() + 4 * o, m, HOP_FRAMES, outs[i].data_ptr())
+                if pcm16 is None:
+                    eng.submit_ptr(s, host.data_ptr() + 4 * o, m, HOP_FRAMES, outs[i].data_ptr())
+                else:
+                    eng.submit_pcm_ptr(s, pcm16.data_ptr() + 2 * o, 1, 1, m, SR, HOP_FRAMES, outs[i].data_ptr())
         for s in range(n_slots):
             eng.wait(s)
 
@@ -250,16 +267,35 @@ def run_ours(args, rank, world, local):
     clocks = sampler.stop() if rank == 0 else None
     d2h_bytes = sum(o.numel() * 4 for o in outs)
 
+    # the same end-to-end leg fed with int16 PCM (bd_submit_pcm_host): reported beside `e2e`, never instead of it
+    pcm16 = torch.from_numpy(np.clip(np.rint(hv * 32768.0), -32768, 32767).astype(np.int16)).pin_memory()
+    e2e_run(2, pcm16)
+    eng.synchronize()
+    if use_dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_run(args.steps, pcm16)
+    eng.synchronize()
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if use_dist:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_pcm16_value = world * hours_per_step * args.steps / float(t.item())
+    del pcm16
+
     # ---------------- per-kernel-family device times (one extra un-graphed pass, CUDA events around every launch)
     prof = eng.profile_device_ptr(d_x.data_ptr(), n, HOP_FRAMES)
     peaks = measured_peaks()
     from buzzdetect_b200.weights import LAYERS
     mma_factor = {"fp16x3": 3, "fp16": 1, "fp32": 0}[args.precision]
     per_layer = {}
-    fam = {"pw_gemm_kernel": {"ms": 0.0, "launches": 0, "flop": 0.0, "bytes": 0.0},
-           "pw_gemm_kernel[layers 7-14]": {"ms": 0.0, "launches": 0, "flop": 0.0, "bytes": 0.0},
-           "sep_fused3_kernel": {"ms": 0.0, "launches": 0, "flop": 0.0, "bytes": 0.0},
-           "depthwise_kernel": {"ms": 0.0, "launches": 0, "flop": 0.0, "bytes": 0.0}}
+    def _f():
+        return {"ms": 0.0, "launches": 0, "flop": 0.0, "bytes": 0.0}
+    # kernel families; a fused separable layer is HBM-bound while K <= 256 (layers 3-6) and tensor-bound at K = 512
+    fam = {"pw_gemm_kernel": _f(), "sep_fused3_kernel[layers 3-7, hbm]": _f(),
+           "sep_fused3_kernel[layers 8-12, tensor]": _f(), "depthwise_kernel": _f()}
     for i, (kind, stride, cin, cout, H, W) in enumerate(LAYERS[1:]):
         v = prof["layers"][f"L{i + 2}"]
         ho, wo = H // stride, W // stride
@@ -275,11 +311,13 @@ def run_ours(args, rank, world, local):
             f = fam["depthwise_kernel"]
             f["ms"] += v["dw_ms"]; f["launches"] += v["dw_launches"]; f["bytes"] += dw_bytes
         if v["pw_launches"]:
-            names = ["sep_fused3_kernel"] if fused else (["pw_gemm_kernel"] + (["pw_gemm_kernel[layers 7-14]"] if i + 2 >= 7 else []))
-            for nm in names:
-                f = fam[nm]
-                f["ms"] += v["pw_ms"]; f["launches"] += v["pw_launches"]; f["flop"] += pw_flop
-                f["bytes"] += ((H * W * cin + ho * wo * cout) * 4.0 * P) if fused else pw_bytes
+            if fused:
+                nm = "sep_fused3_kernel[layers 8-12, tensor]" if cin >= 512 else "sep_fused3_kernel[layers 3-7, hbm]"
+            else:
+                nm = "pw_gemm_kernel"
+            f = fam[nm]
+            f["ms"] += v["pw_ms"]; f["launches"] += v["pw_launches"]; f["flop"] += pw_flop
+            f["bytes"] += ((H * W * cin + ho * wo * cout) * 4.0 * P) if fused else pw_bytes
     l12 = prof["layers"]["L2"]["pw_launches"] == 0 and prof["layers"]["L2"]["dw_launches"] == 0
     if l12:     # layers 1+2 in one kernel: log-mel patch in, layer-2 output out
         fam["l12_fused2_kernel"] = {"ms": prof["conv1"]["ms"], "launches": prof["conv1"]["launches"], "flop": 0.0,
@@ -301,7 +339,7 @@ def run_ours(args, rank, world, local):
     for nm, f in fam.items():
         if f["ms"] <= 0:
             continue
-        tens = nm.startswith("pw_gemm")
+        tens = nm.startswith("pw_gemm") or "tensor" in nm
         ach = (f["flop"] / (f["ms"] / 1e3) / 1e12) if tens else (f["bytes"] / (f["ms"] / 1e3) / 1e9)
         peak = peaks["bf16_tflops_sustained"] if tens else peaks["hbm_gbs"]
         rooflines[nm] = {"bound": "tensor" if tens else "hbm", "achieved": ach, "peak": peak,
@@ -310,17 +348,18 @@ def run_ours(args, rank, world, local):
                          "algorithmic_per_launch": (f["flop"] if tens else f["bytes"]) / max(f["launches"], 1),
                          "avg_launch_ms": f["ms"] / max(f["launches"], 1),
                          "traffic": traffic_tab.get(nm, {}).get("dram_bytes_per_launch")}
+        rooflines[nm]["traffic_source"] = traffic_tab.get("_source") if rooflines[nm]["traffic"] else None
         if tens:
             rooflines[nm]["executed_mma_factor"] = mma_factor
             rooflines[nm]["hbm_gbs"] = f["bytes"] / (f["ms"] / 1e3) / 1e9
-    dominant = max((k for k in rooflines if "[" not in k), key=lambda k: rooflines[k]["ms"])
+    dominant = max(rooflines, key=lambda k: rooflines[k]["ms"])
     roofline = dict(rooflines[dominant])
     roofline["kernel"] = dominant
     roofline["peak_source"] = peaks["source"] + (" bf16 sustained (kernel timed inside a long step)"
                                                 if roofline["bound"] == "tensor" else " copy bandwidth")
-    roofline["note"] = ("algorithmic flops; fp16x3 executes 3 MMAs per algorithmic MMA, and layers 2-6 of this kernel "
-                        "family are HBM-bound (K <= 256): see rooflines['pw_gemm_kernel[layers 7-14]'] for the "
-                        "tensor-bound subset") if roofline["bound"] == "tensor" else "algorithmic bytes (fp32 in + out)"
+    roofline["note"] = ("algorithmic flops (1x); the fp16x3 split executes 3 MMAs per algorithmic MMA, so the ceiling "
+                        "of this mode is one third of the bf16 peak") if roofline["bound"] == "tensor" \
+        else "algorithmic bytes (fp32 in + out)"
     stages = {k: prof[k] for k in ("frontend", "conv1", "depthwise", "pointwise", "pool_head")}
 
     if rank == 0:
@@ -338,7 +377,11 @@ def run_ours(args, rank, world, local):
                        "early_patches": args.early, "late_patches": args.late, "fuse_mask": args.fuse_mask, "sharding": "one file per GPU, no collective"},
             "realtime_factor": value * 3600.0,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": d2h_bytes,
-                    "chunks_per_step": len(chunks), "slots": n_slots},
+                    "chunks_per_step": len(chunks), "slots": n_slots,
+                    "note": "float32 samples from pinned host memory (230 MB per audio-hour: PCIe-bound above ~240 "
+                            "audio-hours/s per GPU)"},
+            "e2e_pcm16": {"value": e2e_pcm16_value, "unit": UNIT, "h2d_bytes_per_step": n * 2,
+                          "d2h_bytes_per_step": d2h_bytes, "entry": "bd_submit_pcm_host (int16 PCM, converted on the device)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,

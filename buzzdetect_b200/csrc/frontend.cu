@@ -65,7 +65,7 @@ __device__ __forceinline__ void dft8(float2 (&v)[8]) {
     v[1] = b0; v[3] = b1; v[5] = b2; v[7] = b3;
 }
 
-__global__ void __launch_bounds__(kWarps * 32) logmel_kernel(const float* __restrict__ x, long long n_valid,
+__global__ void __launch_bounds__(kWarps * 32, 3) logmel_kernel(const float* __restrict__ x, long long n_valid,
                                                              long long frame_begin, int n_frames,
                                                              const FrontendTables* __restrict__ tab,
                                                              float* __restrict__ logmel) {
@@ -103,6 +103,19 @@ __global__ void __launch_bounds__(kWarps * 32) logmel_kernel(const float* __rest
         sincospif(-static_cast<float>(m2 * q1) / 16.0f, &sn, &cs);
         tw2[q1] = make_float2(cs, sn);
     }
+
+    __syncthreads();                                                     // s.win / s.tw512 visible
+    // this lane's window taps (elements 2c, 2c+1 with c = 32 j + lane; zero beyond sample 399) and split-step
+    // twiddles W512^(lane + 32 j): registers instead of 15 shared-memory loads per frame (the kernel is bound by
+    // shared-memory wavefronts, profiles/r1_summary.md)
+    float2 wreg[7], twreg[8];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        const int c = 32 * j + lane;
+        wreg[j] = (j < 6 || lane < 8) ? *reinterpret_cast<const float2*>(s.win + 2 * c) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) twreg[j] = s.tw512[lane + 32 * j];
 
     float2* s1 = s.scratch[warp];
     float2* s2 = s1 + kS1;
@@ -148,8 +161,7 @@ __global__ void __launch_bounds__(kWarps * 32) logmel_kernel(const float* __rest
                 const int c = 32 * j + lane;
                 if (j < 6 || (j == 6 && lane < 8)) {
                     const float2 sv = *reinterpret_cast<const float2*>(xs + 2 * c);
-                    const float2 wv = *reinterpret_cast<const float2*>(s.win + 2 * c);
-                    v[j] = make_float2(sv.x * wv.x, sv.y * wv.y);
+                    v[j] = make_float2(sv.x * wreg[j].x, sv.y * wreg[j].y);
                 } else {
                     v[j] = make_float2(0.f, 0.f);                        // zero padding 400..511
                 }
@@ -192,7 +204,7 @@ __global__ void __launch_bounds__(kWarps * 32) logmel_kernel(const float* __rest
                 const float2 zc = s1[(256 - k) & 255];
                 const float2 xe = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
                 const float2 xo = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
-                const float2 w = s.tw512[k];
+                const float2 w = twreg[j];
                 const float re = xe.x + w.x * xo.x - w.y * xo.y;
                 const float im = xe.y + w.x * xo.y + w.y * xo.x;
                 mag[k] = sqrtf(re * re + im * im);
