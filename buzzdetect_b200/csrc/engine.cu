@@ -63,7 +63,7 @@ struct GraphKey {
 
 struct bd_engine {
     int device = 0, num_sms = 148, precision = BD_PRECISION_FP16X3;
-    int S1 = 1024, S2 = 4096, n_classes = 13;
+    int S1 = 4096, S2 = 4096, n_classes = 13;
     bool use_graph = true;
     cudaStream_t s_compute = nullptr, s_in = nullptr, s_out = nullptr;
     float* d_folded = nullptr;
@@ -439,7 +439,10 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
     e->device = cfg->device;
     e->num_sms = prop.multiProcessorCount;
     e->precision = cfg->precision;
-    e->S1 = cfg->early_patches > 0 ? cfg->early_patches : 1024;
+    // Measured on B200 (profiles/r1_summary.md): with persistent fused kernels the step gets faster all the way up to
+    // one sub-batch per audio-hour (3.48 ms at 1024/4096, 3.34 ms at 4096/4096): tails and launches cost more than L2
+    // residency of the inter-layer activations would win (148..888-patch sub-batches: 3.57-3.80 ms).
+    e->S1 = cfg->early_patches > 0 ? cfg->early_patches : 4096;
     e->S2 = cfg->late_patches > 0 ? cfg->late_patches : 4096;
     e->S2 = std::max(e->S1, (e->S2 / e->S1) * e->S1);           // late batch = whole number of early batches
     e->use_graph = cfg->use_graph != 0;

@@ -285,7 +285,7 @@ l12_fused2_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_con
             const uint32_t lm = lm_u32 + static_cast<uint32_t>(buf * kLmBytes);
             // thread = (channel quad, pair of interior columns): image columns ic0 = 2*pair, ic0 + 1 of tile row tr; the
             // five log-mel columns 2*ic0 .. 2*ic0+4 of a row come from one LDS.128 + one LDS.32
-#pragma unroll 1
+#pragma unroll 2
             for (int item = t >> 3; item < kTileH * 16; item += 16) {
                 const int tr = item >> 4, pair = item & 15;
                 const int ir = r0 - 1 + tr, ic0 = 2 * pair;

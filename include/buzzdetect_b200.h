@@ -66,8 +66,8 @@ typedef struct bd_weights {
 typedef struct bd_config {
     int32_t device;                /* CUDA device ordinal                                                   */
     int32_t precision;             /* BD_PRECISION_*                                                        */
-    int32_t early_patches;         /* patches per sub-batch for frontend..layer 7 depthwise (0 = default)   */
-    int32_t late_patches;          /* patches per sub-batch for layer 7 pointwise..head     (0 = default)   */
+    int32_t early_patches;         /* patches per sub-batch for frontend..layer 7 depthwise (0 = 4096)      */
+    int32_t late_patches;          /* patches per sub-batch for layer 7 pointwise..head     (0 = 4096)      */
     int32_t use_graph;             /* 1 = capture and replay CUDA graphs per (n_samples, hop)               */
     int32_t n_slots;               /* in-flight host chunks for bd_submit_host (1..4, 0 = 2)                */
     int32_t fuse_mask;             /* bit (L-2): run separable layer L as ONE fused depthwise+pointwise kernel
