@@ -570,8 +570,15 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
             const int S = l.late ? e->S2 : e->S1;
             const int M_max = S * l.h_out * l.w_out;
             const char* perr = nullptr;
+            // stand-alone GEMMs of wide layers use 128x256 tiles (an MMA's operand fetch is ~ (4 KB + 32 B x N) / 64 B per
+            // clock: N = 256 amortises the A tile twice as far); the fused kernel wants 128-row weight boxes
+            int bn = 0;
+            {
+                static const int bn_env = [] { const char* v = getenv("BD_PW_BN256"); return v ? atoi(v) : 1; }();
+                if (bn_env && !l.fused_v3 && !l.fused && l.d.cout % 256 == 0 && l.d.cin >= 512) bn = 256;
+            }
             cudaError_t pe = pw_gemm_make_plan(&l.plan, reinterpret_cast<__half*>(H), reinterpret_cast<__half*>(H + plane),
-                                               M_max, l.d.cin, l.w_hi, l.w_lo, l.d.cout, nsplit, 0, out_scale, &perr);
+                                               M_max, l.d.cin, l.w_hi, l.w_lo, l.d.cout, nsplit, bn, out_scale, &perr);
             if (pe != cudaSuccess) return bail(std::string("pointwise plan for layer ") + std::to_string(L + 1) + ": " +
                                                (perr ? perr : cudaGetErrorString(pe)));
         }

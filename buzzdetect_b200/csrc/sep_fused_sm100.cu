@@ -525,7 +525,7 @@ cudaError_t set_attr_f3() {
     if ((e = cudaFuncSetAttribute(sep_fused3_kernel<NSPLIT, STRIDE, NACC, NH>,                             \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax)) != cudaSuccess)  \
         return e;
-    BD_F3_ATTR(128, false) BD_F3_ATTR(256, false) BD_F3_ATTR(512, false) BD_F3_ATTR(512, true)
+    BD_F3_ATTR(128, false) BD_F3_ATTR(256, false) BD_F3_ATTR(512, false) BD_F3_ATTR(512, true) BD_F3_ATTR(256, true)
 #undef BD_F3_ATTR
     return cudaSuccess;
 }
@@ -604,7 +604,9 @@ cudaError_t launch_sep_fused3(const PwGemmPlan& p, const float* X, const float* 
                               cudaStream_t stream) {
     if (P <= 0) return cudaSuccess;
     if (bias_host == nullptr || p.N % 128 != 0) return cudaErrorInvalidValue;
-    const int nacc = p.N >= 512 ? 512 : p.N;             // 128, 256 or 512 accumulator columns per pass
+    static const int nacc_cap = [] { const char* e = getenv("BD_F3_NACC"); return e ? atoi(e) : 512; }();
+    int nacc = p.N >= 512 ? 512 : p.N;                   // 128, 256 or 512 accumulator columns per pass
+    if (nacc > nacc_cap && (nacc_cap == 128 || nacc_cap == 256) && p.N % nacc_cap == 0) nacc = nacc_cap;
     if (nacc != 128 && nacc != 256 && nacc != 512) return cudaErrorInvalidValue;
     const int planes = p.nsplit == 1 ? 1 : 2;
     const int fixed = 1024 + kAStages * planes * kATile + kEpiBytes + kBarBytes;
@@ -648,6 +650,7 @@ cudaError_t launch_sep_fused3(const PwGemmPlan& p, const float* X, const float* 
 #define BD_F3(NS, S)                                                                                             \
     do {                                                                                                         \
         if (prm.nohalo) {                                                                                        \
+            if (nacc == 256) return launch_f3_t<NS, S, 256, true>(map_in, map_c, map_c8, bp, p, prm, smem_bytes, grid, stream); \
             if (nacc != 512) return cudaErrorInvalidValue;                                                       \
             return launch_f3_t<NS, S, 512, true>(map_in, map_c, map_c8, bp, p, prm, smem_bytes, grid, stream);    \
         }                                                                                                        \
