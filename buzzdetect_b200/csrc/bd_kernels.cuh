@@ -106,7 +106,7 @@ bool sep_fused3_supported(int K, int N, int H, int W, int stride);
 // bias_host: the N pointwise biases in HOST memory (kernel parameter = constant bank).
 cudaError_t launch_sep_fused3(const PwGemmPlan& plan, const float* X, const float* dw_w, const float* dw_b,
                               const float* bias_host, float* C, int P, int H, int W, int stride, int num_sms,
-                              cudaStream_t stream);
+                              cudaStream_t stream, bool cta_pairs = false);
 
 // ---- l12_fused_sm100.cu  (layers 1 + 2, warp-specialised: conv1 warps -> stencil warps -> tcgen05 -> epilogue)
 cudaError_t l12_fused2_init_device();

@@ -86,6 +86,7 @@ struct bd_engine {
     bool fuse_conv1 = true;               // layer 1 + layer-2 depthwise in one kernel (conv1_dw2_kernel)
     bool fuse_l12 = true;                 // layers 1 + 2 entirely in one kernel (l12_fused_kernel, tensor-core modes)
     bool l12_v2 = false;                  // ... using the warp-specialised l12_fused2_kernel
+    bool cta_pairs = false;               // sep_fused3 with cta_group::2 MMAs where it applies (BD_FUSE_PAIR)
     const void* dbg_ptr = nullptr;        // bd_debug_stage: where the requested stage's output lives
     bool dbg_planes = false;
     size_t dbg_plane_off = 0;
@@ -196,7 +197,7 @@ int enqueue_chunk(bd_engine* e, const float* x, int64_t n, int hop_frames, float
         const LayerDev& l = e->layers[L];
         if (l.fused_v3)
             BD_CHECK(e, launch_sep_fused3(l.plan, in, l.dw_w, l.dw_b, e->h_folded.data() + l.d.b, out, np, l.d.h_in, l.d.w_in, l.d.stride,
-                                          e->num_sms, st));
+                                          e->num_sms, st, e->cta_pairs));
         else
             BD_CHECK(e, launch_sep_fused(l.plan, in, l.dw_w, l.dw_b, l.b, out, np, l.d.h_in, l.d.w_in, l.d.stride,
                                          e->num_sms, st));
@@ -508,6 +509,7 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
     const bool use_v3 = (cfg_mask & BD_FUSE_V3) != 0;
     e->fuse_conv1 = (cfg_mask & BD_FUSE_CONV1_DW2) != 0;
     e->l12_v2 = e->precision != BD_PRECISION_FP32_SIMT && (cfg_mask & BD_FUSE_L12V2) != 0;
+    e->cta_pairs = (cfg_mask & BD_FUSE_PAIR) != 0;
     e->fuse_l12 = e->precision != BD_PRECISION_FP32_SIMT && (cfg_mask & (BD_FUSE_L12 | BD_FUSE_L12V2)) != 0;
     for (int L = 0; L < BD_N_LAYERS; ++L) {
         LayerDev& l = e->layers[L];

@@ -116,7 +116,7 @@ __device__ __forceinline__ void fma4(float4& acc, const float4& x, const float4&
     acc.w = fmaf(x.w, w.w, acc.w);
 }
 
-template <int NSPLIT, int STRIDE, int NACC, bool NOHALO>
+template <int NSPLIT, int STRIDE, int NACC, bool NOHALO, bool CTA2>
 __global__ void __launch_bounds__(kF3Threads, 1)
 sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_b_hi,
                   const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_c,
@@ -127,7 +127,8 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
     constexpr int kBSlotBytes = kPlanes * kBSlotPlane;
     constexpr int kAccStages = NACC == 512 ? 1 : 2;
     constexpr int kTmemCols = NACC == 128 ? 256 : 512;
-    constexpr int kSlotsPerKb = NACC / kBNs;
+    constexpr int kMmaN = CTA2 ? 2 * kBNs : kBNs;      // CTA pair: each CTA holds 128 of the MMA's 256 weight rows
+    constexpr int kSlotsPerKb = NACC / kMmaN;
     constexpr int BWc = STRIDE == 1 ? 4 : 2;            // stencil block: BWc columns x 2 rows of output pixels
     constexpr int NCW = (BWc - 1) * STRIDE + 3;         // input columns per block row
     constexpr int NRW = STRIDE + 3;                     // input rows per block (2 output rows)
@@ -151,7 +152,14 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int K = prm.K, Ho = prm.Ho, Wo = prm.Wo;
     const int n_groups = prm.N / NACC;
-    const int num_pass = prm.m_tiles * n_groups;        // a pass = (output tile, group of NACC output channels)
+    // a pass = (output tile, group of NACC output channels); a CTA pair walks pairs of adjacent tiles together (the odd
+    // CTA of the last pair may get a tile past the end: its loads are zero-filled and its stores clipped by TMA)
+    const int cta_rank = CTA2 ? static_cast<int>(blockIdx.x & 1) : 0;
+    const bool leader = cta_rank == 0;
+    const int num_pass = (CTA2 ? (prm.m_tiles + 1) / 2 : prm.m_tiles) * n_groups;
+    const int pass0 = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int pass_step = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    auto tile_of = [&](int ps) { return CTA2 ? 2 * (ps / n_groups) + cta_rank : ps / n_groups; };
     const int num_kb = K / kBK;
     const int parts = prm.parts;
     const int in_stages = prm.in_stages;
@@ -168,7 +176,7 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kAStages; ++i) {
-            mbar_init(&a_full[i], 8);                   // every stencil warp arrives once per k-block
+            mbar_init(&a_full[i], CTA2 ? 16 : 8);       // every stencil warp (of both CTAs) arrives once per k-block
             mbar_init(&a_empty[i], 1);
         }
         for (int i = 0; i < kMaxBSlots; ++i) {
@@ -181,11 +189,14 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 128);
+            mbar_init(&tmem_empty[i], CTA2 ? 256 : 128);
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+    if (warp == 2) {
+        if (CTA2) tmem_alloc_pair<kTmemCols>(tmem_slot);
+        else tmem_alloc<kTmemCols>(tmem_slot);
+    }
     if (prm.valid_rows < kBM) {
         // rows the stencil never writes: zero both A stages once (their accumulator rows are discarded, but keep
         // uninitialised bit patterns away from the tensor pipe)
@@ -194,7 +205,8 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
         fence_proxy_async_smem();
     }
     tc_fence_before();
-    __syncthreads();
+    if (CTA2) cluster_sync_all();                       // the peer's barriers are initialised before anyone signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -203,13 +215,22 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
         if (lane == 0) {
             int bs = 0;
             uint32_t bphase = 0;
-            for (int ps = blockIdx.x; ps < num_pass; ps += gridDim.x) {
+            for (int ps = pass0; ps < num_pass; ps += pass_step) {
                 const int n0 = (ps % n_groups) * NACC;
                 for (int kb = 0; kb < num_kb; ++kb) {
 #pragma unroll 1
                     for (int nb = 0; nb < kSlotsPerKb; ++nb) {
                         mbar_wait(&b_empty[bs], bphase ^ 1);
                         unsigned char* dst = b_base + bs * kBSlotBytes;
+                        if (CTA2) {
+                            // both CTAs load their half of the 256-row tile; completion counts on the leader's barrier
+                            const int row = n0 + nb * kMmaN + cta_rank * kBNs;
+                            if (leader) mbar_arrive_expect_tx(&b_full[bs], 2 * kBSlotBytes);
+                            tma_load_2d_pair(dst, &map_b_hi, &b_full[bs], kb * kBK, row);
+                            if (NSPLIT > 1) tma_load_2d_pair(dst + kBSlotPlane, &map_b_lo, &b_full[bs], kb * kBK, row);
+                            if (++bs == b_slots) { bs = 0; bphase ^= 1; }
+                            continue;
+                        }
                         mbar_arrive_expect_tx(&b_full[bs], kBSlotBytes);
                         tma_load_2d(dst, &map_b_hi, &b_full[bs], kb * kBK, n0 + nb * kBNs);
                         if (NSPLIT > 1) tma_load_2d(dst + kBSlotPlane, &map_b_lo, &b_full[bs], kb * kBK, n0 + nb * kBNs);
@@ -232,12 +253,12 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
                     c.part = 0;
                     if (++c.sb == kBK / kCB) {
                         c.sb = 0;
-                        if (++c.kb == num_kb) { c.kb = 0; c.ps += gridDim.x; }
+                        if (++c.kb == num_kb) { c.kb = 0; c.ps += pass_step; }
                     }
                 }
             };
             auto coords = [&](const Cursor& c, int& c0, int& cw, int& ch, int& cp) {
-                const int m_tile = c.ps / n_groups;
+                const int m_tile = tile_of(c.ps);
                 int p0, oh;
                 if (prm.PT == 1) {
                     p0 = m_tile / prm.tiles_per_patch;
@@ -251,7 +272,7 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
                 ch = NOHALO ? 0 : (STRIDE == 1 ? oh - 1 : 2 * oh);
                 cp = p0;
             };
-            Cursor cur{static_cast<int>(blockIdx.x), 0, 0, 0}, pf = cur;
+            Cursor cur{pass0, 0, 0, 0}, pf = cur;
             int c0, cw, ch, cp;
             for (int i = 0; i < prm.prefetch_boxes && pf.ps < num_pass; ++i) {
                 coords(pf, c0, cw, ch, cp);
@@ -280,40 +301,54 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
         // With the loop inside `if (lane == 0)` every address and descriptor lives in per-thread registers and each
         // MMA drags a chain of R2UR moves behind it (~120 clk per issue, measured): with 32-clock N=64 MMAs the
         // tensor pipe then idles three quarters of the time.  Warp-uniform control flow keeps them in uniform registers.
-        {
-            constexpr uint32_t idesc = umma_idesc_f16(kBM, kBNs);
+        if (leader) {
+            constexpr uint32_t idesc = umma_idesc_f16(CTA2 ? 2 * kBM : kBM, kMmaN);
             int stage = 0, bs = 0, acc = 0;
             uint32_t phase = 0, bphase = 0, acc_phase = 0;
-            for (int ps = blockIdx.x; ps < num_pass; ps += gridDim.x) {
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            for (int ps = pass0; ps < num_pass; ps += pass_step) {
+                if (CTA2) mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);
+                else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_acc = tmem_base + static_cast<uint32_t>(acc * NACC);
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&a_full[stage], phase);
+                    if (CTA2) mbar_wait_cluster(&a_full[stage], phase);
+                    else mbar_wait(&a_full[stage], phase);
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(a_base + stage * kAStageBytes);
                     const uint64_t da_hi = umma_desc_k128(a_hi), da_lo = umma_desc_k128(a_hi + kATile);
 #pragma unroll 1
                     for (int nb = 0; nb < kSlotsPerKb; ++nb) {
-                        mbar_wait(&b_full[bs], bphase);
+                        if (CTA2) mbar_wait_cluster(&b_full[bs], bphase);
+                        else mbar_wait(&b_full[bs], bphase);
                         tc_fence_after();
                         const uint32_t b_hi = smem_u32(b_base + bs * kBSlotBytes);
                         const uint64_t db_hi = umma_desc_k128(b_hi), db_lo = umma_desc_k128(b_hi + kBSlotPlane);
-                        const uint32_t d_tmem = d_acc + static_cast<uint32_t>(nb * kBNs);
+                        const uint32_t d_tmem = d_acc + static_cast<uint32_t>(nb * kMmaN);
                         if (elect_one()) {
 #pragma unroll
                             for (int k = 0; k < kBK / 16; ++k) {
                                 const uint64_t koff = static_cast<uint64_t>(k) * 2u;     // 16 fp16 = 32 bytes, >> 4
-                                umma_f16_ss(d_tmem, da_hi + koff, db_hi + koff, idesc, (kb | k) != 0 ? 1u : 0u);
-                                if (NSPLIT > 1) {
-                                    umma_f16_ss(d_tmem, da_lo + koff, db_hi + koff, idesc, 1u);
-                                    umma_f16_ss(d_tmem, da_hi + koff, db_lo + koff, idesc, 1u);
+                                const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+                                if (CTA2) {
+                                    umma_f16_ss_pair(d_tmem, da_hi + koff, db_hi + koff, idesc, accum);
+                                    if (NSPLIT > 1) {
+                                        umma_f16_ss_pair(d_tmem, da_lo + koff, db_hi + koff, idesc, 1u);
+                                        umma_f16_ss_pair(d_tmem, da_hi + koff, db_lo + koff, idesc, 1u);
+                                    }
+                                } else {
+                                    umma_f16_ss(d_tmem, da_hi + koff, db_hi + koff, idesc, accum);
+                                    if (NSPLIT > 1) {
+                                        umma_f16_ss(d_tmem, da_lo + koff, db_hi + koff, idesc, 1u);
+                                        umma_f16_ss(d_tmem, da_hi + koff, db_lo + koff, idesc, 1u);
+                                    }
                                 }
                             }
-                            umma_commit(&b_empty[bs]);
+                            if (CTA2) umma_commit_pair(&b_empty[bs]); else umma_commit(&b_empty[bs]);
                             if (nb == kSlotsPerKb - 1) {
-                                umma_commit(&a_empty[stage]);
-                                if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+                                if (CTA2) umma_commit_pair(&a_empty[stage]); else umma_commit(&a_empty[stage]);
+                                if (kb == num_kb - 1) {
+                                    if (CTA2) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
+                                }
                             }
                         }
                         __syncwarp();
@@ -361,7 +396,7 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
         int stage = 0, is = g;
         uint32_t phase = 0, iphase = 0;
         if (is >= in_stages) { is -= in_stages; iphase ^= 1; }
-        for (int ps = blockIdx.x; ps < num_pass; ps += gridDim.x) {
+        for (int ps = pass0; ps < num_pass; ps += pass_step) {
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait_sleepy(&a_empty[stage], phase ^ 1);
                 const uint32_t a_hi = a_u32 + static_cast<uint32_t>(stage * kAStageBytes);
@@ -424,7 +459,10 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
                 }
                 fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the tensor-core proxy
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&a_full[stage]);
+                if (lane == 0) {
+                    if (CTA2) mbar_arrive_leader(&a_full[stage]);
+                    else mbar_arrive(&a_full[stage]);
+                }
                 if (++stage == kAStages) { stage = 0; phase ^= 1; }
             }
         }
@@ -435,8 +473,8 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
         const int live = prm.valid_rows - q * 32;       // rows of this warp's lane quad that exist (<= 0: none)
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int ps = blockIdx.x; ps < num_pass; ps += gridDim.x) {
-            const int m_tile = ps / n_groups, n0 = (ps - m_tile * n_groups) * NACC;
+        for (int ps = pass0; ps < num_pass; ps += pass_step) {
+            const int m_tile = tile_of(ps), n0 = (ps % n_groups) * NACC;
             int row0;                                    // < 2^31: checked by the launcher
             if (prm.PT == 1) {
                 const int p = m_tile / prm.tiles_per_patch;
@@ -479,17 +517,20 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tmem_empty[acc]);
+            if (CTA2) mbar_arrive_leader(&tmem_empty[acc]);
+            else mbar_arrive(&tmem_empty[acc]);
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
         if (lane == 0) tma_store_wait_all();
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CTA2) cluster_sync_all();                       // nobody leaves while the pair's MMAs may still read its smem
+    else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc<kTmemCols>(tmem_base);
+        if (CTA2) tmem_dealloc_pair<kTmemCols>(tmem_base);
+        else tmem_dealloc<kTmemCols>(tmem_base);
     }
 }
 
@@ -513,19 +554,46 @@ bool encode_4d_f32(CUtensorMap* map, const float* ptr, int C, int W, int H, int 
 template <int NSPLIT, int STRIDE, int NACC, bool NOHALO>
 cudaError_t launch_f3_t(const CUtensorMap& map_in, const CUtensorMap& map_c, const CUtensorMap& map_c8, const BiasParam& bp,
                         const PwGemmPlan& p, const F3Params& prm, int smem_bytes, int grid, cudaStream_t stream) {
-    sep_fused3_kernel<NSPLIT, STRIDE, NACC, NOHALO><<<grid, kF3Threads, smem_bytes, stream>>>(map_in, p.b_hi, p.b_lo,
-                                                                                              map_c, map_c8, bp, prm);
+    sep_fused3_kernel<NSPLIT, STRIDE, NACC, NOHALO, false><<<grid, kF3Threads, smem_bytes, stream>>>(
+        map_in, p.b_hi, p.b_lo, map_c, map_c8, bp, prm);
     return cudaGetLastError();
+}
+
+// CTA-pair launch: clusters of two CTAs (one TPC), grid = an even number of CTAs
+template <int NSPLIT, int STRIDE, int NACC, bool NOHALO>
+cudaError_t launch_f3_pair_t(const CUtensorMap& map_in, const CUtensorMap& map_c, const CUtensorMap& map_c8,
+                             const BiasParam& bp, const PwGemmPlan& p, const F3Params& prm, int smem_bytes, int grid,
+                             cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(kF3Threads);
+    cfg.dynamicSmemBytes = static_cast<size_t>(smem_bytes);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, sep_fused3_kernel<NSPLIT, STRIDE, NACC, NOHALO, true>, map_in, p.b_hi, p.b_lo, map_c,
+                              map_c8, bp, prm);
 }
 
 template <int NSPLIT, int STRIDE>
 cudaError_t set_attr_f3() {
     cudaError_t e;
 #define BD_F3_ATTR(NACC, NH)                                                                               \
-    if ((e = cudaFuncSetAttribute(sep_fused3_kernel<NSPLIT, STRIDE, NACC, NH>,                             \
+    if ((e = cudaFuncSetAttribute(sep_fused3_kernel<NSPLIT, STRIDE, NACC, NH, false>,                      \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax)) != cudaSuccess)  \
         return e;
     BD_F3_ATTR(128, false) BD_F3_ATTR(256, false) BD_F3_ATTR(512, false) BD_F3_ATTR(512, true) BD_F3_ATTR(256, true)
+    if ((e = cudaFuncSetAttribute(sep_fused3_kernel<NSPLIT, STRIDE, 512, true, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax)) != cudaSuccess)
+        return e;
+    if ((e = cudaFuncSetAttribute(sep_fused3_kernel<NSPLIT, STRIDE, 256, false, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax)) != cudaSuccess)
+        return e;
 #undef BD_F3_ATTR
     return cudaSuccess;
 }
@@ -601,7 +669,7 @@ bool sep_fused3_supported(int K, int N, int H, int W, int stride) {
 
 cudaError_t launch_sep_fused3(const PwGemmPlan& p, const float* X, const float* dw_w, const float* dw_b,
                               const float* bias_host, float* C, int P, int H, int W, int stride, int num_sms,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, bool cta_pairs) {
     if (P <= 0) return cudaSuccess;
     if (bias_host == nullptr || p.N % 128 != 0) return cudaErrorInvalidValue;
     static const int nacc_cap = [] { const char* e = getenv("BD_F3_NACC"); return e ? atoi(e) : 512; }();
@@ -640,7 +708,17 @@ cudaError_t launch_sep_fused3(const PwGemmPlan& p, const float* X, const float* 
     const long long passes = static_cast<long long>(prm.m_tiles) * (p.N / nacc);
     const long long m_rows = static_cast<long long>(P) * prm.Ho * prm.Wo;
     if (passes >= (1LL << 31) || m_rows + kBM >= (1LL << 31)) return cudaErrorInvalidValue;
-    const int grid = static_cast<int>(passes < num_sms ? passes : num_sms);
+    int grid = static_cast<int>(passes < num_sms ? passes : num_sms);
+    // CTA pairs (cta_group::2: one MMA of M = 256, N = 256 per pair, each CTA holding half of the weight tile).
+    // Parity-tested, but measured SLOWER than the one-CTA kernel on B200 (layers 8-12: 0.218 vs 0.187 ms per
+    // audio-hour, layer 6: 0.305 vs 0.213): the pair couples two stencil / epilogue pipelines behind one issuer and the
+    // peer's half of B does not arrive faster than a second local copy would.  Opt-in (BD_FUSE_PAIR / BD_F3_PAIR=1).
+    static const int pair_env = [] { const char* e = getenv("BD_F3_PAIR"); return e ? atoi(e) : 0; }();
+    const bool pair = (cta_pairs || pair_env != 0) && num_sms >= 2 && nacc >= 256 && passes >= 2;
+    if (pair) {
+        const long long pair_passes = (static_cast<long long>(prm.m_tiles) + 1) / 2 * (p.N / nacc);
+        grid = static_cast<int>(2 * pair_passes < num_sms ? 2 * pair_passes : num_sms);
+    }
     CUtensorMap map_in, map_c, map_c8;
     if (!encode_4d_f32(&map_in, X, p.K, W, H, P, kCB, prm.BW, prm.BH, prm.PB)) return cudaErrorUnknown;   // box <= tensor in nohalo mode
     if (!encode_store_map_f32(&map_c, C, m_rows, p.N, 32) || !encode_store_map_f32(&map_c8, C, m_rows, p.N, 8))
@@ -649,6 +727,10 @@ cudaError_t launch_sep_fused3(const PwGemmPlan& p, const float* X, const float* 
     for (int i = 0; i < kMaxN; ++i) bp.v[i] = i < p.N ? bias_host[i] : 0.f;
 #define BD_F3(NS, S)                                                                                             \
     do {                                                                                                         \
+        if (pair && prm.nohalo && nacc == 512)                                                                   \
+            return launch_f3_pair_t<NS, S, 512, true>(map_in, map_c, map_c8, bp, p, prm, smem_bytes, grid & ~1, stream); \
+        if (pair && !prm.nohalo && nacc == 256)                                                                  \
+            return launch_f3_pair_t<NS, S, 256, false>(map_in, map_c, map_c8, bp, p, prm, smem_bytes, grid & ~1, stream); \
         if (prm.nohalo) {                                                                                        \
             if (nacc == 256) return launch_f3_t<NS, S, 256, true>(map_in, map_c, map_c8, bp, p, prm, smem_bytes, grid, stream); \
             if (nacc != 512) return cudaErrorInvalidValue;                                                       \

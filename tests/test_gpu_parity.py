@@ -133,7 +133,8 @@ def _median_threshold(a):
     ("fp16x3", 96, 199.68, -1), ("fp16", 96, 61.3, -1), ("fp16x3", 96, 61.3, 0), ("fp16x3", 48, 33.1, 0x7FF),
     ("fp16x3", 48, 33.1, 0x10002), ("fp16", 96, 20.0, 0x20000), ("fp16x3", 96, 61.3, 0x5003E),
     ("fp16x3", 48, 33.1, 0x507FF), ("fp16x3", 96, 61.3, 0xC0006), ("fp16x3", 48, 33.1, 0xC0006),
-    ("fp16x3", 96, 61.3, 0x10002),
+    ("fp16x3", 96, 61.3, 0x10002), ("fp16x3", 96, 61.3, 0x1D07DE), ("fp16x3", 48, 33.1, 0x1D07FE),
+    ("fp16", 96, 20.0, 0x1D07DE),
 ])
 def test_predict_matches_oracle(engines, yamnet_variables, mel, head, precision, hop, seconds, fuse_mask):
     e = engines(precision, early_patches=16, late_patches=48, fuse_mask=fuse_mask)   # several early / late sub-batches
