@@ -115,9 +115,31 @@ cudaError_t launch_l12_fused2(const PwGemmPlan& plan, const float* logmel, int h
                               const float* b1, const float* dw_w, const float* dw_b, const float* bias_host, float* C,
                               int num_sms, cudaStream_t stream);
 
-// ---- resample.cu
+// K-major fp16 operand map (SWIZZLE_128B, [box_rows x 64] boxes) over a row-major [rows, cols] plane
+bool encode_kmajor_f16_map(CUtensorMap* map, const void* ptr, int rows, int cols, int box_rows);
+
+// ---- resample.cu  (tap-by-tap CUDA-core evaluation: equal-rate downmix, chunk tails, fallback)
+// Computes out[m] for m in [m_begin, n_out).
 cudaError_t launch_resample(const void* in, int in_fmt /*0 f32, 1 s16*/, int channels, long long n_in_frames,
                             int up, int down, const float* taps, int taps_per_phase, float* out, long long n_out,
-                            cudaStream_t stream);
+                            cudaStream_t stream, long long m_begin = 0);
+
+// ---- resample_tc_sm100.cu  (the same filter as a tcgen05 GEMM over blocks of NB outputs; see the file header)
+struct ResampleTcPlan {
+    int up, down, T;          // rational ratio, taps per phase
+    int NB;                   // outputs per block (a multiple of up and of 32)
+    int ntile, n_tiles;       // columns per pass (<= 160), passes per row tile
+    int S;                    // input samples between blocks
+    int K;                    // window length padded to a multiple of 64
+    float out_scale;          // inverse of the power-of-two scale applied to H before the fp16 split
+    CUtensorMap b_hi, b_lo;   // H planes [NB, K]
+};
+cudaError_t resample_tc_init_device();
+bool resample_tc_geometry(int up, int down, int taps_per_phase, ResampleTcPlan* plan);
+void resample_tc_build_matrix(const ResampleTcPlan& plan, const float* taps /*[T][up]*/, float* H /*[NB][K]*/);
+// Writes out[0 .. n_done) with n_done = (n_out / NB) * NB; the caller finishes [n_done, n_out) with launch_resample.
+cudaError_t launch_resample_tc(const ResampleTcPlan& plan, const void* in, int in_fmt, int channels,
+                               long long n_in_frames, float* out, long long n_out, int num_sms, cudaStream_t stream,
+                               long long* n_done);
 
 }  // namespace bd

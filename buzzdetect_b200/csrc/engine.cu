@@ -99,7 +99,15 @@ struct bd_engine {
     std::vector<cudaEvent_t> prof_events;
     std::vector<int> prof_cat;
     // resampler filter cache: (src_rate) -> device taps
-    struct Resampler { int up, down, taps_per_phase; float* d_taps; };
+    struct Resampler {
+        int up, down, taps_per_phase;
+        float* d_taps;
+        bool tc_ok = false;               // tensor-core formulation available (resample_tc_sm100.cu)
+        ResampleTcPlan tc;
+        __half* d_h_hi = nullptr;
+        __half* d_h_lo = nullptr;
+    };
+    bool tc_resample = true;              // BD_FUSE_NO_TC_RESAMPLE clears it
     std::map<int, Resampler> resamplers;
     std::string last_error;
 };
@@ -404,7 +412,7 @@ void bd_engine_destroy(bd_engine* e) {
         if (s.ev_out) cudaEventDestroy(s.ev_out);
     }
     for (auto& l : e->layers) { cudaFree(l.w_hi); cudaFree(l.w_lo); }
-    for (auto& kv : e->resamplers) cudaFree(kv.second.d_taps);
+    for (auto& kv : e->resamplers) { cudaFree(kv.second.d_taps); cudaFree(kv.second.d_h_hi); cudaFree(kv.second.d_h_lo); }
     cudaFree(e->d_folded); cudaFree(e->d_tab); cudaFree(e->d_headW); cudaFree(e->d_headB);
     cudaFree(e->d_logmel); cudaFree(e->d_F_early2); cudaFree(e->d_F_late2); cudaFree(e->d_F_early); cudaFree(e->d_H_early); cudaFree(e->d_F_late); cudaFree(e->d_H_late);
     if (e->s_compute) cudaStreamDestroy(e->s_compute);
@@ -463,6 +471,7 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
     if (e->precision != BD_PRECISION_FP32_SIMT) BD_CREATE(pw_gemm_init_device());
     if (e->precision != BD_PRECISION_FP32_SIMT) BD_CREATE(sep_fused3_init_device());
     if (e->precision != BD_PRECISION_FP32_SIMT) BD_CREATE(l12_fused2_init_device());
+    BD_CREATE(resample_tc_init_device());
 
     // ---- weights
     e->h_folded.assign(w->folded, w->folded + w->folded_len);
@@ -510,6 +519,7 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
     e->fuse_conv1 = (cfg_mask & BD_FUSE_CONV1_DW2) != 0;
     e->l12_v2 = e->precision != BD_PRECISION_FP32_SIMT && (cfg_mask & BD_FUSE_L12V2) != 0;
     e->cta_pairs = (cfg_mask & BD_FUSE_PAIR) != 0;
+    e->tc_resample = (cfg_mask & BD_FUSE_NO_TC_RESAMPLE) == 0;
     e->fuse_l12 = e->precision != BD_PRECISION_FP32_SIMT && (cfg_mask & (BD_FUSE_L12 | BD_FUSE_L12V2)) != 0;
     for (int L = 0; L < BD_N_LAYERS; ++L) {
         LayerDev& l = e->layers[L];
@@ -786,10 +796,42 @@ static int get_resampler(bd_engine* e, int src_rate, bd_engine::Resampler** out)
         r.up = up; r.down = down; r.taps_per_phase = tpp; r.d_taps = nullptr;
         BD_CHECK(e, cudaMalloc(&r.d_taps, taps.size() * sizeof(float)));
         BD_CHECK(e, cudaMemcpy(r.d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+        // the same filter as a [blocks x K] x [K x NB] GEMM: H holds, for each of the NB outputs of a block, its taps laid
+        // along the block's input window (resample_tc_sm100.cu)
+        if (resample_tc_geometry(up, down, tpp, &r.tc)) {
+            const size_t nh = static_cast<size_t>(r.tc.NB) * r.tc.K;
+            std::vector<float> H(nh);
+            resample_tc_build_matrix(r.tc, taps.data(), H.data());
+            std::vector<__half> hi(nh), lo(nh);
+            r.tc.out_scale = split_weights_f16(H.data(), nh, hi.data(), lo.data());
+            BD_CHECK(e, cudaMalloc(&r.d_h_hi, nh * sizeof(__half)));
+            BD_CHECK(e, cudaMalloc(&r.d_h_lo, nh * sizeof(__half)));
+            BD_CHECK(e, cudaMemcpy(r.d_h_hi, hi.data(), nh * sizeof(__half), cudaMemcpyHostToDevice));
+            BD_CHECK(e, cudaMemcpy(r.d_h_lo, lo.data(), nh * sizeof(__half), cudaMemcpyHostToDevice));
+            r.tc_ok = encode_kmajor_f16_map(&r.tc.b_hi, r.d_h_hi, r.tc.NB, r.tc.K, r.tc.ntile) &&
+                      encode_kmajor_f16_map(&r.tc.b_lo, r.d_h_lo, r.tc.NB, r.tc.K, r.tc.ntile);
+        }
         BD_CHECK(e, cudaDeviceSynchronize());   // the tap upload is not stream-ordered with s_compute
         it = e->resamplers.emplace(src_rate, r).first;
     }
     *out = &it->second;
+    return 0;
+}
+
+// downmix + resample of one chunk on `st`: tensor-core GEMM for the whole blocks, tap-by-tap kernel for the tail (and for
+// equal rates, where only the downmix / int16 conversion is left)
+static int run_resample(bd_engine* e, const bd_engine::Resampler* r, const void* d_in, int fmt, int channels,
+                        long long n_frames, float* d_out, long long no, cudaStream_t st) {
+    long long done = 0;
+    if (r->tc_ok && e->tc_resample && r->d_taps != nullptr) {
+        BD_CHECK(e, launch_resample_tc(r->tc, d_in, fmt, channels, n_frames, d_out, no, e->num_sms, st, &done));
+        if (done > 0) e->launch_count++;
+    }
+    if (done < no) {
+        BD_CHECK(e, launch_resample(d_in, fmt, channels, n_frames, r->up, r->down, r->d_taps, r->taps_per_phase, d_out, no,
+                                    st, done));
+        e->launch_count++;
+    }
     return 0;
 }
 
@@ -806,9 +848,7 @@ int32_t bd_resample_device(bd_engine* e, const void* d_in, int32_t fmt, int32_t 
     bd_engine::Resampler ident{1, 1, 1, nullptr};
     bd_engine::Resampler* r = &ident;
     if (src_rate != 16000 && get_resampler(e, src_rate, &r)) return 1;
-    BD_CHECK(e, launch_resample(d_in, fmt, channels, n_frames, r->up, r->down, r->d_taps, r->taps_per_phase, d_out, no,
-                                e->s_compute));
-    e->launch_count++;
+    if (run_resample(e, r, d_in, fmt, channels, n_frames, d_out, no, e->s_compute)) return 1;
     BD_CHECK(e, cudaStreamSynchronize(e->s_compute));
     return 0;
 }
@@ -845,9 +885,7 @@ int32_t bd_submit_pcm_host(bd_engine* e, int32_t slot, const void* pcm, int32_t 
     if (n_frames > 0) BD_CHECK(e, cudaMemcpyAsync(s.d_pcm, pcm, pcm_bytes, cudaMemcpyHostToDevice, e->s_in));
     BD_CHECK(e, cudaEventRecord(s.ev_in, e->s_in));
     BD_CHECK(e, cudaStreamWaitEvent(e->s_compute, s.ev_in, 0));
-    BD_CHECK(e, launch_resample(s.d_pcm, fmt, channels, n_frames, r->up, r->down, r->d_taps, r->taps_per_phase, s.d_in, n,
-                                e->s_compute));
-    e->launch_count++;
+    if (run_resample(e, r, s.d_pcm, fmt, channels, n_frames, s.d_in, n, e->s_compute)) return 1;
     if (run_chunk(e, s.d_in, n, hop_frames, s.d_act, emb ? s.d_emb : nullptr, P)) return 1;
     BD_CHECK(e, cudaEventRecord(s.ev_comp, e->s_compute));
     BD_CHECK(e, cudaStreamWaitEvent(e->s_out, s.ev_comp, 0));

@@ -759,6 +759,10 @@ TensorMapEncodeFn tensor_map_encode_fn() {
     return fn;
 }
 
+bool encode_kmajor_f16_map(CUtensorMap* map, const void* ptr, int rows, int cols, int box_rows) {
+    return encode_2d_f16(map, ptr, rows, cols, box_rows);
+}
+
 bool encode_store_map_f32(CUtensorMap* map, float* ptr, long long rows, int cols, int box_rows) {
     TensorMapEncodeFn fn = tensor_map_encode_fn();
     if (fn == nullptr || cols % 32 != 0 || rows < 1 || box_rows < 8 || box_rows % 8) return false;

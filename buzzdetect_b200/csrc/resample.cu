@@ -39,8 +39,8 @@ __device__ __forceinline__ float load_mono(const void* in, int channels, long lo
 template <int FMT>
 __global__ void __launch_bounds__(256) resample_kernel(const void* __restrict__ in, int channels, long long n_in,
                                                        int up, int down, const float* __restrict__ taps, int T,
-                                                       float* __restrict__ out, long long n_out) {
-    for (long long m = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; m < n_out;
+                                                       float* __restrict__ out, long long n_out, long long m_begin) {
+    for (long long m = m_begin + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; m < n_out;
          m += static_cast<long long>(gridDim.x) * blockDim.x) {
         if (taps == nullptr) {                       // equal rates: downmix / convert only
             out[m] = load_mono<FMT>(in, channels, m);
@@ -63,16 +63,17 @@ __global__ void __launch_bounds__(256) resample_kernel(const void* __restrict__ 
 }  // namespace
 
 cudaError_t launch_resample(const void* in, int in_fmt, int channels, long long n_in_frames, int up, int down,
-                            const float* taps, int taps_per_phase, float* out, long long n_out, cudaStream_t stream) {
-    if (n_out <= 0) return cudaSuccess;
-    long long g = (n_out + 255) / 256;
+                            const float* taps, int taps_per_phase, float* out, long long n_out, cudaStream_t stream,
+                            long long m_begin) {
+    if (n_out <= m_begin) return cudaSuccess;
+    long long g = (n_out - m_begin + 255) / 256;
     if (g > 148LL * 32) g = 148LL * 32;
     if (in_fmt == 0)
         resample_kernel<0><<<static_cast<int>(g), 256, 0, stream>>>(in, channels, n_in_frames, up, down, taps,
-                                                                    taps_per_phase, out, n_out);
+                                                                    taps_per_phase, out, n_out, m_begin);
     else
         resample_kernel<1><<<static_cast<int>(g), 256, 0, stream>>>(in, channels, n_in_frames, up, down, taps,
-                                                                    taps_per_phase, out, n_out);
+                                                                    taps_per_phase, out, n_out, m_begin);
     return cudaGetLastError();
 }
 

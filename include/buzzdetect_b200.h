@@ -42,6 +42,7 @@ extern "C" {
 #define BD_FUSE_V3 (1 << 18)          /* fuse_mask bit: fused layers use sep_fused3_kernel (TMA-staged stencil input) where it applies */
 #define BD_FUSE_L12V2 (1 << 19)       /* fuse_mask bit: layers 1+2 in one warp-specialised kernel (l12_fused2_kernel) */
 #define BD_FUSE_PAIR (1 << 20)        /* fuse_mask bit: sep_fused3 issues cta_group::2 MMAs from CTA pairs (N >= 256 layers) */
+#define BD_FUSE_NO_TC_RESAMPLE (1 << 21) /* fuse_mask bit: resample tap by tap on CUDA cores instead of the tcgen05 GEMM */
 #define BD_PRECISION_FP16X3 3      /* tcgen05, hi/lo fp16 split, 3 MMAs: float32-equivalent (default)    */
 
 typedef struct bd_engine bd_engine;

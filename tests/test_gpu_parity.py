@@ -254,6 +254,21 @@ def test_full_size_prefix_and_padding_properties(engines):
     assert a.shape[0] == P and np.array_equal(a, b)
 
 
+def test_full_size_tensor_core_path_agrees_with_cuda_core_path(engines):
+    """BASELINE configs[1] size: the default plan (fused tcgen05 kernels, fp16 hi/lo split) against the float32 CUDA-core
+    mode of the same engine -- two disjoint sets of kernels -- on one hour of audio, default sub-batches."""
+    x = np.tile(O.synth_audio(60 * 16000, seed=78), 60)
+    a = engines("fp16x3").predict(x, 96)
+    b = engines("fp32").predict(x, 96)
+    assert a.shape == b.shape == (3750, 13)
+    err = float(np.abs(a - b).max())
+    _report("full_size_fp16x3_vs_fp32", {"max_abs": err, "cells_rounded_differently": int((np.round(a, 2) != np.round(b, 2)).sum())})
+    assert err <= 1e-3, err
+    thr = float(np.median(b[:, 8]))
+    near = np.abs(b[:, 8] - thr) <= 1e-3
+    assert int(((a[:, 8] > thr) != (b[:, 8] > thr))[~near].sum()) == 0
+
+
 def test_day_long_single_call_has_no_index_overflow(engines):
     """configs[2] scale in ONE call: 24 h = 1.3824e9 samples (5.5 GB, byte offsets beyond 2**32).  The signal repeats
     every 15360 samples, so all 90000 frames but the last (which sees the zero padding) must be bit-identical."""

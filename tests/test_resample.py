@@ -44,14 +44,19 @@ def test_downmix_matches_numpy_mean():
     assert np.array_equal(R.downmix(xi), np.mean(xi.astype(np.float32) / np.float32(32768.0), axis=1))
 
 
+NO_TC = 1 << 21        # BD_FUSE_NO_TC_RESAMPLE: tap-by-tap CUDA-core evaluation instead of the tcgen05 GEMM
+
+
 @pytest.mark.gpu
+@pytest.mark.parametrize("tc", [True, False])
 @pytest.mark.parametrize("sr,ch,dtype", [(44100, 2, np.int16), (44100, 1, np.float32), (32000, 1, np.float32),
                                          (48000, 2, np.float32), (22050, 1, np.int16), (8000, 1, np.float32),
-                                         (16000, 2, np.int16), (16000, 1, np.float32)])
-def test_cuda_resampler_matches_oracle(engines, sr, ch, dtype):
-    e = engines("fp32")
+                                         (16000, 2, np.int16), (16000, 1, np.float32), (96000, 3, np.int16),
+                                         (11025, 1, np.float32), (24000, 2, np.int16)])
+def test_cuda_resampler_matches_oracle(engines, sr, ch, dtype, tc):
+    e = engines("fp32") if tc else engines("fp32", fuse_mask=NO_TC)
     rng = np.random.default_rng(sr + ch)
-    n = int(sr * 0.35) + 17
+    n = int(sr * (2.35 if tc else 0.35)) + 17                  # the GEMM path needs several whole blocks to be exercised
     t = np.arange(n) / sr
     sig = 0.4 * np.sin(2 * np.pi * 440.0 * t)[:, None] + 0.2 * rng.standard_normal((n, ch))
     if dtype == np.int16:
@@ -66,7 +71,23 @@ def test_cuda_resampler_matches_oracle(engines, sr, ch, dtype):
     if sr == 16000:
         assert np.array_equal(got, want)                      # identity / pure downmix: bit exact
     else:
-        assert np.abs(got - want).max() < 5e-6
+        err = float(np.abs(got - want).max())
+        assert err < 5e-6, err
+
+
+@pytest.mark.gpu
+def test_tensor_core_resampler_equals_tap_by_tap_kernel(engines):
+    """Same filter, two evaluations: the GEMM (fp16 hi/lo split, fp32 accumulate) against the CUDA-core loop on 20 s of
+    44.1 kHz stereo int16 -- including the first block (zero state before the chunk) and the tail after the last whole
+    block, which the GEMM path hands to the tap-by-tap kernel."""
+    rng = np.random.default_rng(9)
+    n = 44100 * 20 + 123
+    x = np.clip(rng.standard_normal((n, 2)) * 6000, -32768, 32767).astype(np.int16)
+    a = engines("fp32").resample(x, 44100)
+    b = engines("fp32", fuse_mask=NO_TC).resample(x, 44100)
+    assert a.shape == b.shape
+    assert float(np.abs(a - b).max()) < 2e-6
+    assert np.array_equal(a[-(a.size % 160):], b[-(b.size % 160):])        # the tail is the same kernel
 
 
 @pytest.mark.gpu
