@@ -285,6 +285,29 @@ def run_ours(args, rank, world, local):
     e2e_pcm16_value = world * hours_per_step * args.steps / float(t.item())
     del pcm16
 
+    # ---------------- the stage in front of the path for non-16 kHz input (BASELINE configs[2]): downmix + resample of
+    # one audio-hour of 44.1 kHz stereo int16 PCM already in HBM (synchronous C-ABI call, wall clock around it)
+    resample_stage = None
+    if not args.no_resample:
+        n441 = 3600 * 44100
+        g_ = torch.Generator(device="cuda").manual_seed(7 + rank)
+        pcm441 = (torch.randn((n441, 2), device="cuda", generator=g_) * 3000).to(torch.int16)
+        n_rs = capi.load_library().bd_resample_out_len(n441, 44100)
+        d_rs = torch.empty(int(n_rs) + 256, dtype=torch.float32, device="cuda")
+        for _ in range(2):
+            eng.resample_device_ptr(pcm441.data_ptr(), 1, 2, n441, 44100, d_rs.data_ptr(), d_rs.numel())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            eng.resample_device_ptr(pcm441.data_ptr(), 1, 2, n441, 44100, d_rs.data_ptr(), d_rs.numel())
+        rs_ms = (time.perf_counter() - t0) / reps * 1e3
+        rs_bytes = n441 * 2 * 2 + int(n_rs) * 4
+        resample_stage = {"ms_per_audio_hour": rs_ms, "input": "44.1 kHz stereo int16, device-resident",
+                          "algorithmic_gbs": rs_bytes / (rs_ms / 1e3) / 1e9, "frac_hbm": rs_bytes / (rs_ms / 1e3) / 1e9 / measured_peaks()["hbm_gbs"],
+                          "kernel": "resample_tc_kernel (tcgen05 GEMM over blocks of 160 outputs) + resample_kernel tail"}
+        del pcm441, d_rs
+
     # ---------------- per-kernel-family device times (one extra un-graphed pass, CUDA events around every launch)
     prof = eng.profile_device_ptr(d_x.data_ptr(), n, HOP_FRAMES)
     peaks = measured_peaks()
@@ -387,6 +410,7 @@ def run_ours(args, rank, world, local):
             "roofline": roofline,
             "rooflines": rooflines,
             "stages": stages,
+            "resample_stage": resample_stage,
             "layers": per_layer,
             "whole_path_tflops": TOTAL_FLOP_PER_PATCH * P * world * args.steps / (ms_max / 1000.0) / 1e12,
         }
@@ -415,6 +439,7 @@ def main():
     ap.add_argument("--fuse-mask", dest="fuse_mask", type=int, default=-1,
                     help="bit (L-2): run separable layer L as one fused depthwise+pointwise kernel (-1 = default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-resample", dest="no_resample", action="store_true", help="skip the 44.1 kHz resample-stage timing")
     args = ap.parse_args()
     rank, world, local = dist_setup(args.gpus)
     if args.impl == "reference":

@@ -303,6 +303,14 @@ class Engine:
                     "bd_resample_host")
         return out[:got.value]
 
+    def resample_device_ptr(self, d_in: int, fmt: int, channels: int, n_frames: int, src_rate: int, d_out: int,
+                            out_capacity: int) -> int:
+        """Device-resident PCM in (fmt 0 float32 / 1 int16, interleaved), float32 mono at 16 kHz out; synchronous."""
+        got = C.c_int64()
+        self._check(self._lib.bd_resample_device(self._h, d_in, fmt, channels, n_frames, src_rate, d_out, out_capacity,
+                                                 C.byref(got)), "bd_resample_device")
+        return got.value
+
     # ------------------------------------------------------------------ test hooks
     def debug_logmel(self, samples: np.ndarray, n_frames: int) -> np.ndarray:
         x = np.ascontiguousarray(samples, dtype=np.float32)

@@ -52,34 +52,62 @@ struct RsParams {
     float out_scale;
 };
 
+// one sample, any channel count, with the chunk's zero state outside [0, n_in)
 template <int FMT>
-__device__ __forceinline__ float load_mono(const void* in, int channels, long long n_in, long long idx) {
-    if (idx < 0 || idx >= n_in) return 0.f;                     // zero state per chunk
+__device__ __forceinline__ float load_mono_checked(const void* in, int channels, long long n_in, long long idx) {
+    if (idx < 0 || idx >= n_in) return 0.f;
+    float s = 0.f;
     if (FMT == 0) {
         const float* p = static_cast<const float*>(in) + idx * channels;
         if (channels == 1) return __ldg(p);
-        if (channels == 2) {
-            const float2 v = __ldg(reinterpret_cast<const float2*>(p));
-            return (v.x + v.y) / 2.0f;
-        }
-        float s = 0.f;
         for (int c = 0; c < channels; ++c) s += __ldg(p + c);
-        return s / static_cast<float>(channels);
     } else {
         const short* p = static_cast<const short*>(in) + idx * channels;
         const float k = 1.0f / 32768.0f;
         if (channels == 1) return static_cast<float>(__ldg(p)) * k;
-        if (channels == 2) {
-            const short2 v = __ldg(reinterpret_cast<const short2*>(p));
-            return (static_cast<float>(v.x) * k + static_cast<float>(v.y) * k) / 2.0f;
-        }
-        float s = 0.f;
         for (int c = 0; c < channels; ++c) s += static_cast<float>(__ldg(p + c)) * k;
-        return s / static_cast<float>(channels);
     }
+    return s / static_cast<float>(channels);
 }
 
-template <int FMT>
+// eight consecutive mono samples starting at s0.  CH = 1 / 2: straight-line code for the interior (the common case: no
+// branches between the loads, so a thread keeps all of them in flight); CH = 0: any channel count.
+template <int FMT, int CH>
+__device__ __forceinline__ void load8(const void* in, int channels, long long n_in, long long s0, float (&x)[8]) {
+    if (CH != 0 && s0 >= 0 && s0 + 8 <= n_in) {
+        const float k = 1.0f / 32768.0f;
+        if (FMT == 1 && CH == 2) {
+            const int* p = static_cast<const int*>(in) + s0;                 // one int = (left, right) int16
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int v = __ldg(p + j);
+                const float l = static_cast<float>(static_cast<short>(v & 0xFFFF)) * k;
+                const float r = static_cast<float>(static_cast<short>(v >> 16)) * k;
+                x[j] = (l + r) / 2.0f;
+            }
+        } else if (FMT == 1) {
+            const short* p = static_cast<const short*>(in) + s0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = static_cast<float>(__ldg(p + j)) * k;
+        } else if (CH == 2) {
+            const float2* p = static_cast<const float2*>(in) + s0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float2 v = __ldg(p + j);
+                x[j] = (v.x + v.y) / 2.0f;
+            }
+        } else {
+            const float* p = static_cast<const float*>(in) + s0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = __ldg(p + j);
+        }
+        return;
+    }
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) x[j] = load_mono_checked<FMT>(in, channels, n_in, s0 + j);
+}
+
+template <int FMT, int CH>
 __global__ void __launch_bounds__(kThreads, 1)
 resample_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                    const __grid_constant__ CUtensorMap map_c, const RsParams prm) {
@@ -109,7 +137,7 @@ resample_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_co
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kAStages; ++i) {
-            mbar_init(&a_full[i], 8);
+            mbar_init(&a_full[i], 4);                   // the four warps of the producer group that owns the stage
             mbar_init(&a_empty[i], 1);
         }
         for (int i = 0; i < kBSlots; ++i) {
@@ -183,39 +211,53 @@ resample_tc_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_co
         }
     } else if (warp >= 8) {
         // ================================================================= A producers: input windows -> A tile
-        const int tp = threadIdx.x - 256;
+        // Two groups of four warps take alternate k-blocks (= alternate A stages), and a thread issues the 32 loads of
+        // four items before it converts any of them: the stage is bound by load latency, not by instruction count.
+        const int g = (warp - 8) >> 2;
+        const int tp = threadIdx.x - 256 - g * 128;
         const uint32_t a_u32 = smem_u32(a_base);
-        int stage = 0;
         uint32_t phase = 0;
+        unsigned gk = 0;                                 // k-blocks issued so far by this CTA (all passes): stage = gk & 1
         for (int ps = blockIdx.x; ps < num_pass; ps += gridDim.x) {
             const long long row_base = static_cast<long long>(ps / prm.n_tiles) * kBM;
-            for (int kb = 0; kb < num_kb; ++kb) {
+            for (int kb = 0; kb < num_kb; ++kb, ++gk) {
+                const int stage = static_cast<int>(gk & 1u);
+                if (stage != g) continue;
                 mbar_wait_sleepy(&a_empty[stage], phase ^ 1);
                 const uint32_t a_hi = a_u32 + static_cast<uint32_t>(stage * kAStageBytes), a_lo = a_hi + kATile;
 #pragma unroll 1
-                for (int it = 0; it < 4; ++it) {
-                    const int item = tp + 256 * it;
-                    const int kk = item >> 3, ch = item & 7;                 // tile row, 8-sample chunk of the k-block
-                    const long long s0 = (row_base + kk) * prm.S - prm.lead + kb * kBK + ch * 8;
-                    __half2 hi[4], lo[4];
+                for (int batch = 0; batch < 2; ++batch) {
+                    float x[4][8];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float x0 = load_mono<FMT>(prm.in, prm.channels, prm.n_in, s0 + 2 * j);
-                        const float x1 = load_mono<FMT>(prm.in, prm.channels, prm.n_in, s0 + 2 * j + 1);
-                        const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-                        hi[j] = __halves2half2(h0, h1);
-                        lo[j] = __halves2half2(__float2half_rn(x0 - __half2float(h0)), __float2half_rn(x1 - __half2float(h1)));
+                    for (int it = 0; it < 4; ++it) {
+                        const int item = tp + 128 * (batch * 4 + it);
+                        const int kk = item >> 3, ch = item & 7;             // tile row, 8-sample chunk of the k-block
+                        const long long s0 = (row_base + kk) * prm.S - prm.lead + kb * kBK + ch * 8;
+                        load8<FMT, CH>(prm.in, prm.channels, prm.n_in, s0, x[it]);
                     }
-                    const uint32_t off = static_cast<uint32_t>((kk >> 3) * 1024 + (kk & 7) * 128 + ((ch ^ (kk & 7)) << 4));
-                    const uint32_t* ph = reinterpret_cast<const uint32_t*>(hi);
-                    const uint32_t* pl = reinterpret_cast<const uint32_t*>(lo);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int item = tp + 128 * (batch * 4 + it);
+                        const int kk = item >> 3, ch = item & 7;
+                        __half2 hi[4], lo[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float x0 = x[it][2 * j], x1 = x[it][2 * j + 1];
+                            const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+                            hi[j] = __halves2half2(h0, h1);
+                            lo[j] = __halves2half2(__float2half_rn(x0 - __half2float(h0)), __float2half_rn(x1 - __half2float(h1)));
+                        }
+                        const uint32_t off = static_cast<uint32_t>((kk >> 3) * 1024 + (kk & 7) * 128 + ((ch ^ (kk & 7)) << 4));
+                        const uint32_t* ph = reinterpret_cast<const uint32_t*>(hi);
+                        const uint32_t* pl = reinterpret_cast<const uint32_t*>(lo);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
+                    }
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_full[stage]);
-                if (++stage == kAStages) { stage = 0; phase ^= 1; }
+                phase ^= 1;
             }
         }
     } else if (warp >= 4) {
@@ -275,9 +317,14 @@ long long gcd_ll(long long a, long long b) { while (b) { long long t = a % b; a 
 }  // namespace
 
 cudaError_t resample_tc_init_device() {
-    cudaError_t e = cudaFuncSetAttribute(resample_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(resample_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e;
+#define BD_RS_ATTR(F, C)                                                                                          \
+    if ((e = cudaFuncSetAttribute(resample_tc_kernel<F, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)) != \
+        cudaSuccess)                                                                                              \
+        return e;
+    BD_RS_ATTR(0, 0) BD_RS_ATTR(0, 1) BD_RS_ATTR(0, 2) BD_RS_ATTR(1, 0) BD_RS_ATTR(1, 1) BD_RS_ATTR(1, 2)
+#undef BD_RS_ATTR
+    return cudaSuccess;
 }
 
 bool resample_tc_geometry(int up, int down, int taps_per_phase, ResampleTcPlan* g) {
@@ -331,10 +378,14 @@ cudaError_t launch_resample_tc(const ResampleTcPlan& g, const void* in, int in_f
     if (!encode_store_map_f32(&map_c, out, rows, g.NB, 32)) return cudaErrorUnknown;
     const long long passes = static_cast<long long>(prm.m_tiles) * prm.n_tiles;
     const int grid = static_cast<int>(passes < num_sms ? passes : num_sms);
-    if (in_fmt == 0)
-        resample_tc_kernel<0><<<grid, kThreads, kSmemBytes, stream>>>(g.b_hi, g.b_lo, map_c, prm);
-    else
-        resample_tc_kernel<1><<<grid, kThreads, kSmemBytes, stream>>>(g.b_hi, g.b_lo, map_c, prm);
+#define BD_RS_LAUNCH(F, C) resample_tc_kernel<F, C><<<grid, kThreads, kSmemBytes, stream>>>(g.b_hi, g.b_lo, map_c, prm)
+    const int chsel = channels == 1 ? 1 : (channels == 2 ? 2 : 0);
+    if (in_fmt == 0) {
+        if (chsel == 1) BD_RS_LAUNCH(0, 1); else if (chsel == 2) BD_RS_LAUNCH(0, 2); else BD_RS_LAUNCH(0, 0);
+    } else {
+        if (chsel == 1) BD_RS_LAUNCH(1, 1); else if (chsel == 2) BD_RS_LAUNCH(1, 2); else BD_RS_LAUNCH(1, 0);
+    }
+#undef BD_RS_LAUNCH
     *n_done = rows * g.NB;
     return cudaGetLastError();
 }
