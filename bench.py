@@ -352,7 +352,7 @@ def run_ours(args, rank, world, local):
                             "bytes": FRONTEND_BYTES_PER_PATCH * float(P)}
     total_prof_ms = sum(prof[k]["ms"] for k in ("frontend", "conv1", "depthwise", "pointwise", "pool_head"))
     traffic_tab = {}
-    tpath = os.path.join(ROOT, "profiles", "traffic_r1d.json")
+    tpath = os.path.join(ROOT, "profiles", "traffic_r1e.json")
     if not os.path.exists(tpath):
         tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
     if os.path.exists(tpath):
