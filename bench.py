@@ -154,6 +154,35 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(dev: int):
+    """Best effort: run this rank (and allocate its pinned buffers) on the CPUs of the NUMA node the GPU hangs off, so
+    that eight ranks do not pull their host->device traffic through one socket.  Returns a note for the JSON line."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(dev), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip()
+        if not out:
+            return "numa: no pci bus id"
+        bus = out.lower()                                         # 00000000:1b:00.0 -> 0000:1b:00.0
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return "numa: single node"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return f"numa: node {node} has no allowed cpus"
+        os.sched_setaffinity(0, allowed)
+        return f"numa: bound to node {node} ({len(allowed)} cpus)"
+    except Exception as exc:                                          # noqa: BLE001 -- diagnostics only
+        return f"numa: not bound ({type(exc).__name__})"
+
+
 # ----------------------------------------------------------------------------------------------- our arm
 def run_ours(args, rank, world, local):
     import numpy as np
@@ -185,6 +214,7 @@ def run_ours(args, rank, world, local):
 
     dev = local if use_dist else 0
     torch.cuda.set_device(dev)
+    numa_note = bind_to_gpu_numa_node(dev) if use_dist else "numa: single rank, not bound"
     eng = capi.Engine(device=dev, precision=args.precision, early_patches=args.early, late_patches=args.late,
                       n_slots=4, fuse_mask=args.fuse_mask)
     hours_per_step = args.hours
@@ -397,7 +427,8 @@ def run_ours(args, rank, world, local):
                        "patches_per_step_per_gpu": P, "pointwise_precision": args.precision,
                        "weights": eng.weights_provenance.split(":")[0],
                        "l2": "input (230 MB/step) larger than L2; no explicit flush", "e2e_chunk_s": args.chunk_s,
-                       "early_patches": args.early, "late_patches": args.late, "fuse_mask": args.fuse_mask, "sharding": "one file per GPU, no collective"},
+                       "early_patches": args.early, "late_patches": args.late, "fuse_mask": args.fuse_mask,
+                       "sharding": "one file per GPU, no collective", "host": numa_note},
             "realtime_factor": value * 3600.0,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": d2h_bytes,
                     "chunks_per_step": len(chunks), "slots": n_slots,
