@@ -65,6 +65,24 @@ def test_ffmpeg_decoder_reads_pcm_wav_exactly():
         audio.decode_file(WAV + ".missing")
 
 
+def test_ffmpeg_decoder_keeps_channels(tmp_path):
+    """Packed stereo PCM comes back as [n, 2] float32 in file order (queue_chunk downmixes afterwards)."""
+    audio = _ffmpeg_or_skip()
+    rng = np.random.default_rng(1)
+    x = (rng.standard_normal((4410, 2)) * 5000).astype("<i2")
+    p = os.path.join(str(tmp_path), "st.wav")
+    with wave.open(p, "wb") as w:
+        w.setnchannels(2)
+        w.setsampwidth(2)
+        w.setframerate(44100)
+        w.writeframes(x.tobytes())
+    y, sr = audio.decode_file(p)
+    assert sr == 44100 and y.shape == (4410, 2)
+    assert np.array_equal(y, x.astype(np.float32) / 32768.0)
+    t = pipeline.DecodedTrack(p)
+    assert t.channels == 2 and t.read(10).shape == (10, 2)
+
+
 @pytest.mark.skipif(not os.path.exists(MP3), reason="reference checkout not present (GPU box)")
 def test_mp3_decode_reproduces_the_fixture():
     audio = _ffmpeg_or_skip()
