@@ -76,6 +76,25 @@ def test_cuda_resampler_matches_oracle(engines, sr, ch, dtype, tc):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("sr,ch", [(12000, 1), (37800, 2), (88200, 2), (192000, 1), (6000, 1), (47999, 1)])
+def test_unusual_rates_both_evaluations_agree(engines, sr, ch):
+    """Rates with other up/down factors (block sizes 32..160 x n-tiles, up-sampling, and one ratio whose interpolation
+    factor is too large for either table: both paths must refuse it the same way)."""
+    rng = np.random.default_rng(sr)
+    n = int(sr * 1.7) + 5
+    x = (rng.standard_normal((n, ch)) * 0.2).astype(np.float32)
+    x = x[:, 0] if ch == 1 else x
+    if sr == 47999:
+        with pytest.raises(RuntimeError, match="unsupported sample-rate ratio"):
+            engines("fp32").resample(x, sr)
+        return
+    a = engines("fp32").resample(x, sr)
+    b = engines("fp32", fuse_mask=NO_TC).resample(x, sr)
+    assert a.shape == b.shape == (R.out_len(n, sr),)
+    assert np.isfinite(a).all() and float(np.abs(a - b).max()) < 2e-6
+
+
+@pytest.mark.gpu
 def test_tensor_core_resampler_equals_tap_by_tap_kernel(engines):
     """Same filter, two evaluations: the GEMM (fp16 hi/lo split, fp32 accumulate) against the CUDA-core loop on 20 s of
     44.1 kHz stereo int16 -- including the first block (zero state before the chunk) and the tail after the last whole
