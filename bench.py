@@ -423,7 +423,7 @@ def run_ours(args, rank, world, local):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision != "fp16" else "f16",
             "data": "synthetic",
             "config": {"workload": f"synthetic {hours_per_step:g}-hour 16 kHz mono recording per GPU, YAMNet + "
-                                   "model_general_v3, hop 1 (BASELINE configs[1])",
+                                   f"model_general_v3, hop {HOP_FRAMES / 96:g} (BASELINE configs[{1 if HOP_FRAMES == 96 else 4}])",
                        "patches_per_step_per_gpu": P, "pointwise_precision": args.precision,
                        "weights": eng.weights_provenance.split(":")[0],
                        "l2": "input (230 MB/step) larger than L2; no explicit flush", "e2e_chunk_s": args.chunk_s,
@@ -455,6 +455,7 @@ def run_ours(args, rank, world, local):
 
 
 def main():
+    global HOP_FRAMES
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -469,9 +470,12 @@ def main():
     ap.add_argument("--late", type=int, default=0)
     ap.add_argument("--fuse-mask", dest="fuse_mask", type=int, default=-1,
                     help="bit (L-2): run separable layer L as one fused depthwise+pointwise kernel (-1 = default)")
+    ap.add_argument("--hop-frames", dest="hop_frames", type=int, default=96,
+                    help="96 = framehop_prop 1 (headline), 48 = 0.5 (BASELINE configs[4], yamnet_k2 halfhop)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-resample", dest="no_resample", action="store_true", help="skip the 44.1 kHz resample-stage timing")
     args = ap.parse_args()
+    HOP_FRAMES = args.hop_frames
     rank, world, local = dist_setup(args.gpus)
     if args.impl == "reference":
         run_reference(args, rank, world)
