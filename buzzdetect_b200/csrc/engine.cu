@@ -2,12 +2,14 @@
 //
 // One engine = one inferer (reference: one model instance per WorkerInferer thread, src/inference/worker.py:21).
 // A chunk of 16 kHz audio goes through
-//     frontend -> conv1 -> 13 x (depthwise -> pointwise) -> mean(H,W) -> dense head
-// in sub-batches sized so that every inter-layer activation stays resident in the 126 MB L2:
+//     frontend -> layers 1+2 (one kernel) -> fused depthwise+pointwise kernels (layers 3-6, 8-12) and
+//     depthwise / GEMM pairs (layers 7, 13, 14) -> mean(H,W) -> dense head
+// in sub-batches that bound the working set independently of the chunk length:
 //   * "early" phase (frontend .. layer-7 depthwise, up to 384 KB of activations per patch): early_patches at a time
 //   * "late"  phase (layer-7 pointwise .. head, <= 48 KB per patch): late_patches at a time
-// The same small buffers are re-used by every sub-batch, so dirty lines are overwritten in L2 instead of being
-// written back; HBM traffic is essentially the audio in and the activations out.
+// Both default to 4096 patches (1.09 audio-hours): measured, large sub-batches beat L2-resident small ones because
+// kernel tails and launches cost more than the HBM round trips they would save (profiles/r1_summary.md).
+// The whole chunk is captured into a CUDA graph per (buffer, length, hop) and replayed.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>

@@ -14,7 +14,12 @@
 //   warp 1   : MMA issuer    -- one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16),
 //              tcgen05.commit releases smem slots and publishes the accumulator
 //   warp 2   : TMEM allocator (2 accumulator stages x BN columns)
-//   warps 4-7: epilogue      -- tcgen05.ld 32x32b -> +bias, ReLU -> float32 stores (row-contiguous 128 B runs)
+//   warps 4-7: epilogue      -- tcgen05.ld 32x32b -> scale, +bias, ReLU -> smem transpose -> coalesced float4 stores
+//
+// Used by the stand-alone GEMMs of layers 7, 13, 14 (default plan) and by every layer when fusion is switched off.
+// This file also holds the first-generation fused kernels (sep_fused_kernel: register-fed stencil producers;
+// l12_fused_kernel: layers 1+2 behind CTA-wide barriers), kept selectable through fuse_mask and parity-tested; the
+// default plan uses sep_fused_sm100.cu and l12_fused_sm100.cu instead.
 #include <cmath>
 
 #include "bd_common.cuh"

@@ -11,6 +11,9 @@
  *   bd_predict_device    same, for audio already resident in HBM (bench "value", chunk pipelines)
  *   bd_submit_host /     same as bd_predict_host but split so a caller can keep several chunks in flight
  *   bd_wait              (H2D of chunk i+1 overlaps compute of chunk i); replaces N analyzer threads
+ *   bd_submit_pcm_host   the same for a chunk still in its decoded form (int16 / float32 PCM at the file's rate):
+ *                        WorkerStreamer.queue_chunk's downmix + resample (src/stream/worker.py:110-129) run on the
+ *                        device in front of predict
  *   bd_resample_*        librosa.resample call in src/stream/worker.py:128 (+ np.mean downmix :116-117)
  *   bd_profile_device    per-stage device times (the reference only has wall-clock `rate`, worker.py:54-65)
  *   bd_debug_*           test hooks: individual kernels against the oracle
