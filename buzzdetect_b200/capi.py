@@ -5,9 +5,11 @@ fallback: if the shared library is missing, or no sm_100 device is present, cons
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 import os
 import threading
+import weakref
 
 import numpy as np
 
@@ -61,6 +63,12 @@ SIGNATURES = {
     "bd_submit_pcm_host": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32,
                                        C.c_int32, C.c_void_p, C.c_void_p, _i64p]),
     "bd_wait": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "bd_flush": (C.c_int32, [C.c_void_p]),
+    "bd_set_auto_flush": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "bd_slot_state": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "bd_batch_stats": (C.c_int32, [C.c_void_p, _i64p, _i64p]),
+    "bd_host_alloc": (C.c_int32, [C.c_size_t, C.c_int32, C.POINTER(C.c_void_p)]),
+    "bd_host_free": (None, [C.c_void_p]),
     "bd_synchronize": (C.c_int32, [C.c_void_p]),
     "bd_profile_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, _f32p, _i64p]),
     "bd_launch_count": (C.c_int64, [C.c_void_p]),
@@ -128,12 +136,59 @@ def _ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def pinned_empty(shape, dtype=np.float32, write_combined: bool = False) -> np.ndarray:
+    """numpy array over pinned (page-locked) host memory from bd_host_alloc: what the streamer's chunk ring is made of.
+    The memory is released when the last view of the array is garbage collected.  Needs a CUDA device."""
+    lib = load_library()
+    shape = (int(shape),) if np.isscalar(shape) else tuple(int(d) for d in shape)
+    dt = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
+    p = C.c_void_p()
+    if lib.bd_host_alloc(max(nbytes, 1), 1 if write_combined else 0, C.byref(p)) or not p.value:
+        msg = lib.bd_last_error(None)
+        raise RuntimeError("bd_host_alloc: " + (msg.decode(errors="replace") if msg else "failed"))
+    buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+    weakref.finalize(buf, lib.bd_host_free, p.value)
+    return np.frombuffer(buf, dtype=dt, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+
+
+class Ticket:
+    """One chunk in flight (bd_submit_* ... bd_wait).  result() blocks until the activations are on the host; until
+    then the ticket keeps the input buffer alive (the DMA engine may still be reading it)."""
+
+    __slots__ = ("_eng", "slot", "act", "emb", "n_samples", "_keep", "_done", "_lock", "__weakref__")
+
+    def __init__(self, eng, slot, act, emb, n_samples, keep):
+        self._eng, self.slot, self.act, self.emb, self.n_samples, self._keep = eng, slot, act, emb, n_samples, keep
+        self._done = False
+        self._lock = threading.Lock()
+
+    def done(self) -> bool:
+        return self._done
+
+    def wait(self):
+        with self._lock:
+            if not self._done:
+                try:
+                    self._eng._wait_slot(self.slot)
+                finally:
+                    self._done = True
+                    self._keep = None
+                    self._eng._release(self)
+        return self
+
+    def result(self):
+        self.wait()
+        return self.act if self.emb is None else (self.act, self.emb)
+
+
 class Engine:
     """One inferer: YAMNet frontend + MobileNet-v1 + dense head resident on one B200."""
 
     def __init__(self, device: int = 0, yamnet_variables: dict | None = None, embedder: str = "yamnet_k2",
                  head: tuple | None = None, precision: str | None = None, early_patches: int = 0,
-                 late_patches: int = 0, use_graph: bool = True, n_slots: int = 2, fuse_mask: int = -1):
+                 late_patches: int = 0, use_graph: bool = True, n_slots: int = 2, fuse_mask: int = -1,
+                 allow_synthetic: bool | None = None, max_inflight_samples: int = 1 << 27):
         self._h = None
         lib = load_library()
         self._lib = lib
@@ -142,7 +197,7 @@ class Engine:
             raise ValueError(f"precision must be one of {sorted(PRECISION)}")
         self.precision = precision
         if yamnet_variables is None:
-            yamnet_variables, self.weights_provenance = W.resolve_yamnet()
+            yamnet_variables, self.weights_provenance = W.resolve_yamnet(allow_synthetic=allow_synthetic)
         else:
             self.weights_provenance = "caller"
         folded = W.fold_yamnet(yamnet_variables)
@@ -176,7 +231,13 @@ class Engine:
         if lib.bd_engine_create(C.byref(cfg), C.byref(w), C.byref(h), err, 512):
             raise RuntimeError("bd_engine_create: " + err.value.decode(errors="replace"))
         self._h = h
-        self.n_slots = n_slots
+        self.n_slots = max(1, min(int(n_slots) if n_slots > 0 else 2, 64))
+        # ticket API (submit / submit_pcm): free slots, tickets in submission order, in-flight budget
+        self._tk_lock = threading.Lock()
+        self._free = list(range(self.n_slots - 1, -1, -1))
+        self._outstanding = collections.deque()
+        self._inflight_samples = 0
+        self.max_inflight_samples = int(max_inflight_samples)
 
     # ------------------------------------------------------------------ plumbing
     def _check(self, rc, what):
@@ -186,6 +247,10 @@ class Engine:
 
     def close(self):
         if getattr(self, "_h", None):
+            try:
+                self.drain()
+            except Exception:
+                pass
             self._lib.bd_engine_destroy(self._h)
             self._h = None
 
@@ -202,17 +267,107 @@ class Engine:
     # ------------------------------------------------------------------ hot path
     def predict(self, samples: np.ndarray, hop_frames: int = 96, want_embeddings: bool = False):
         """Host numpy in, host numpy out: [P, n_classes] (and [P,1024])."""
+        return self.submit(samples, hop_frames, want_embeddings).result()
+
+    # ------------------------------------------------------------------ tickets: chunks in flight
+    def _wait_slot(self, slot: int):
+        self._check(self._lib.bd_wait(self._h, slot), "bd_wait")
+
+    def _release(self, tk: "Ticket"):
+        with self._tk_lock:
+            try:
+                self._outstanding.remove(tk)
+            except ValueError:
+                pass
+            self._inflight_samples -= tk.n_samples
+            self._free.append(tk.slot)
+
+    def _acquire_slot(self, n_samples: int) -> int:
+        """A free slot; completes the oldest tickets first when every slot is taken or the in-flight budget is spent
+        (back-pressure on the submitting thread, like the reference's bounded q_analyze)."""
+        while True:
+            with self._tk_lock:
+                over = self._outstanding and self._inflight_samples + n_samples > self.max_inflight_samples
+                if self._free and not over:
+                    self._inflight_samples += n_samples
+                    return self._free.pop()
+                oldest = self._outstanding[0] if self._outstanding else None
+            if oldest is None:
+                raise RuntimeError("no free slot: slots are held through the raw submit_ptr/wait API")
+            oldest.wait()
+
+    def _register(self, slot, act, emb, n_samples, keep) -> "Ticket":
+        tk = Ticket(self, slot, act, emb, n_samples, keep)
+        with self._tk_lock:
+            self._outstanding.append(tk)
+        return tk
+
+    def submit(self, samples: np.ndarray, hop_frames: int = 96, want_embeddings: bool = False) -> "Ticket":
+        """Queue one 16 kHz mono float32 chunk; returns at once (pinned input) with a Ticket.  Chunks queued while the
+        GPU is busy run together as one pass (include/buzzdetect_b200.h, "Chunk coalescing")."""
         x = np.ascontiguousarray(samples, dtype=np.float32)
         if x.ndim != 1:
             raise ValueError("samples must be 1-D (mono, 16 kHz)")
         _, _, P = frames_for(x.size, hop_frames)
         act = np.empty((P, self.n_classes), dtype=np.float32)
         emb = np.empty((P, EMBED_DIM), dtype=np.float32) if want_embeddings else None
-        npat = C.c_int64()
-        self._check(self._lib.bd_predict_host(self._h, _ptr(x), x.size, hop_frames, _ptr(act),
-                                              _ptr(emb) if emb is not None else None, C.byref(npat)), "bd_predict_host")
-        assert npat.value == P
-        return (act, emb) if want_embeddings else act
+        slot = self._acquire_slot(x.size)
+        tk = self._register(slot, act, emb, x.size, x)
+        try:
+            got = self.submit_ptr(slot, x.ctypes.data, x.size, hop_frames, act.ctypes.data,
+                                  emb.ctypes.data if emb is not None else None)
+        except Exception:
+            tk._done = True
+            self._release(tk)
+            raise
+        assert got == P
+        return tk
+
+    def submit_pcm(self, pcm: np.ndarray, src_rate: int, hop_frames: int = 96) -> "Ticket":
+        """Queue one chunk still in its decoded form: [n] or [n, channels], int16 or float32 at src_rate."""
+        a = np.asarray(pcm)
+        fmt = 1 if a.dtype == np.int16 else 0
+        if fmt == 0:
+            a = a.astype(np.float32, copy=False)
+        a = np.ascontiguousarray(a)
+        ch = 1 if a.ndim == 1 else a.shape[1]
+        n_out = int(self._lib.bd_resample_out_len(a.shape[0], src_rate))
+        _, _, P = frames_for(n_out, hop_frames)
+        act = np.empty((P, self.n_classes), dtype=np.float32)
+        slot = self._acquire_slot(n_out)
+        tk = self._register(slot, act, None, n_out, a)
+        try:
+            got = self.submit_pcm_ptr(slot, a.ctypes.data, fmt, ch, a.shape[0], src_rate, hop_frames, act.ctypes.data)
+        except Exception:
+            tk._done = True
+            self._release(tk)
+            raise
+        assert got == P
+        return tk
+
+    def set_auto_flush(self, on: bool):
+        """False: submitted chunks are only launched by flush() / a ticket's wait() (deterministic batches)."""
+        self._check(self._lib.bd_set_auto_flush(self._h, 1 if on else 0), "bd_set_auto_flush")
+
+    def flush(self):
+        """Launch every chunk that is still waiting for company (does not wait for results)."""
+        self._check(self._lib.bd_flush(self._h), "bd_flush")
+
+    def drain(self):
+        """Complete every outstanding ticket (results stay readable through the tickets)."""
+        while True:
+            with self._tk_lock:
+                tk = self._outstanding[0] if self._outstanding else None
+            if tk is None:
+                return
+            tk.wait()
+
+    @property
+    def batch_stats(self) -> tuple[int, int]:
+        """(CNN passes launched through the slot API, chunks they carried)."""
+        b, c = C.c_int64(), C.c_int64()
+        self._check(self._lib.bd_batch_stats(self._h, C.byref(b), C.byref(c)), "bd_batch_stats")
+        return b.value, c.value
 
     def predict_ptr(self, host_ptr: int, n: int, hop_frames: int, act_ptr: int, emb_ptr: int | None = None) -> int:
         npat = C.c_int64()
@@ -243,14 +398,7 @@ class Engine:
             a = a.astype(np.float32, copy=False)
         a = np.ascontiguousarray(a)
         ch = 1 if a.ndim == 1 else a.shape[1]
-        n_out = int(self._lib.bd_resample_out_len(a.shape[0], src_rate))
-        _, _, P = frames_for(n_out, hop_frames)
-        act = np.empty((P, self.n_classes), dtype=np.float32)
-        self.wait(0)
-        got = self.submit_pcm_ptr(0, a.ctypes.data, fmt, ch, a.shape[0], src_rate, hop_frames, act.ctypes.data)
-        self.wait(0)
-        assert got == P
-        return act
+        return self.submit_pcm(a, src_rate, hop_frames).result()
 
     def wait(self, slot: int):
         self._check(self._lib.bd_wait(self._h, slot), "bd_wait")

@@ -33,6 +33,21 @@ cudaError_t frontend_init_device();
 cudaError_t launch_logmel(const float* x, long long n_valid, long long frame_begin, int n_frames,
                           const FrontendTables* tab, float* logmel, int num_sms, cudaStream_t stream);
 
+// ---- frontend2.cu  (version 2: 16 x 16 FFT across half-warps, lane = frame mel, TMA in/out, segment table)
+constexpr int kMaxLogmelSegs = 64;
+struct LogmelSeg {                 // one independent chunk of 16 kHz audio inside a batched launch
+    const float* x;                // device samples
+    long long n_valid;             // samples that exist (reads beyond are the virtual zero padding of pad_waveform)
+    long long frame_begin;         // first STFT frame to compute (frame f covers samples 160 f .. 160 f + 399)
+    int row_begin;                 // first row of the shared log-mel buffer this segment writes
+    int n_rows;                    // number of frames
+};
+struct FrontendMelParam { unsigned char raw[2880]; };   // opaque image of the kernel's mel parameter block
+cudaError_t frontend2_init_device();
+void frontend2_build_mel(const FrontendTables& tab, FrontendMelParam* out);
+cudaError_t launch_logmel_segs(const LogmelSeg* segs, int n_segs, const FrontendMelParam& mel, const float* window,
+                               float* logmel, long long logmel_rows, int num_sms, cudaStream_t stream);
+
 // ---- layers.cu
 // conv 3x3 stride 2 SAME (pad 0 before / 1 after), 1 -> 32 channels, folded BN + ReLU.  in: log-mel rows, patch p
 // starts at row p*hop_frames of `logmel` (patches are views, never copied).  out: [P,48,32,32] float32 NHWC.

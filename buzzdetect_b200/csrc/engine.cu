@@ -50,8 +50,20 @@ struct Slot {
     float* d_act = nullptr;
     float* d_emb = nullptr;
     int64_t out_cap = 0;            // patches
+    // results leave the device through pinned staging owned by the slot (a device->host copy into pageable memory
+    // would block the submitting thread until the chunk's compute has finished); bd_wait copies them to the caller
+    float* h_act = nullptr;
+    float* h_emb = nullptr;
+    int64_t h_act_cap = 0, h_emb_cap = 0;   // floats
+    float* user_act = nullptr;      // where bd_wait delivers (nullptr: the copy went straight to the caller's pinned buffer)
+    float* user_emb = nullptr;
+    float* dst_act = nullptr;       // destination of the device->host copies (caller's pinned buffer or the staging)
+    float* dst_emb = nullptr;
+    int64_t n = 0, P = 0;
+    int hop = 0;
+    bool want_emb = false;
     cudaEvent_t ev_in = nullptr, ev_comp = nullptr, ev_out = nullptr;
-    bool busy = false;
+    int state = 0;                  // 0 free, 1 pending (input on its way, compute not enqueued), 2 launched
 };
 
 struct GraphKey {
@@ -93,6 +105,20 @@ struct bd_engine {
     bool dbg_planes = false;
     size_t dbg_plane_off = 0;
     std::vector<Slot> slots;
+    std::vector<int> pending;             // slots submitted but not yet launched, in submission order
+    std::recursive_mutex mu;                       // the slot API may be driven by two threads (inferer submits, writer waits)
+    // coalesced batches (several small chunks in ONE pass of the CNN): outputs of the whole batch, double-buffered
+    float* d_act_batch[2] = {nullptr, nullptr};
+    float* d_emb_batch[2] = {nullptr, nullptr};
+    cudaEvent_t ev_batch_out[2] = {nullptr, nullptr};
+    int batch_set = 0;
+    cudaEvent_t ev_last_comp = nullptr;   // end of the most recently enqueued compute (GPU-idle test for auto-flush)
+    bool any_launched = false;
+    int64_t batches = 0, batched_chunks = 0;
+    bool auto_flush = true;               // bd_set_auto_flush(0): chunks wait until bd_wait / bd_flush (tests, batch drivers)
+    int64_t coalesce_target = 3072;       // pending patches that trigger a launch even while the GPU is busy
+    FrontendMelParam mel_param;
+    bool frontend_v1 = false;             // BD_FRONTEND_V1=1: the round-1 kernel (A/B measurements)
     std::map<GraphKey, cudaGraphExec_t> graphs;
     std::map<GraphKey, int64_t> graph_launches;
     int64_t launch_count = 0;
@@ -168,7 +194,44 @@ void mark(bd_engine* e, int cat, cudaStream_t st) {
 // Enqueue the whole chunk on `st`.  x: device audio, n samples.  Outputs are device pointers.
 // stop_stage >= 0 (debug): stop after that stage of the FIRST early sub-batch (see bd_debug_stage); the location of
 // the stage's output is left in e->dbg_*.
-int enqueue_chunk(bd_engine* e, const float* x, int64_t n, int hop_frames, float* d_act, float* d_emb,
+// What the frontend reads in one pass: ONE chunk (n_segs == 0: x / n; the chunk may span several late batches), or a
+// coalesced batch of whole chunks (n_segs > 0; P = patch slots of the whole batch <= late_patches).  In a batch, chunk c
+// owns the patch slots [g_c, g_c + P_c) and the log-mel rows from g_c * hop on; with overlapping patches (hop < 96) the
+// slot after a chunk's last patch straddles two chunks and its output is never read.
+struct FrontJob {
+    const float* x = nullptr;
+    int64_t n = 0;
+    int n_segs = 0;
+    LogmelSeg segs[kMaxLogmelSegs];
+};
+
+int run_frontend(bd_engine* e, const FrontJob& job, int64_t big, int nb, int hop_frames, cudaStream_t st) {
+    const int n_fr = (nb - 1) * hop_frames + kPatchFrames;
+    const long long cap_rows = static_cast<long long>(e->S2) * kPatchFrames;
+    if (job.n_segs == 0) {
+        if (e->frontend_v1) {
+            BD_CHECK(e, launch_logmel(job.x, job.n, big * hop_frames, n_fr, e->d_tab, e->d_logmel, e->num_sms, st));
+        } else {
+            LogmelSeg sg{job.x, job.n, big * hop_frames, 0, n_fr};
+            BD_CHECK(e, launch_logmel_segs(&sg, 1, e->mel_param, e->d_tab->window, e->d_logmel, cap_rows, e->num_sms, st));
+        }
+        return 0;
+    }
+    if (big != 0) return fail(e, "internal: a coalesced batch must fit one late batch");
+    if (e->frontend_v1) {
+        for (int i = 0; i < job.n_segs; ++i) {
+            const LogmelSeg& sg = job.segs[i];
+            BD_CHECK(e, launch_logmel(sg.x, sg.n_valid, sg.frame_begin, sg.n_rows, e->d_tab,
+                                      e->d_logmel + static_cast<size_t>(sg.row_begin) * kMel, e->num_sms, st));
+        }
+    } else {
+        BD_CHECK(e, launch_logmel_segs(job.segs, job.n_segs, e->mel_param, e->d_tab->window, e->d_logmel, cap_rows,
+                                       e->num_sms, st));
+    }
+    return 0;
+}
+
+int enqueue_chunk(bd_engine* e, const FrontJob& job, int hop_frames, float* d_act, float* d_emb,
                   int64_t P, cudaStream_t st, int stop_stage = -1) {
     const int prec = e->precision;
     const int dw_mode = prec == BD_PRECISION_FP32_SIMT ? 0 : (prec == BD_PRECISION_FP16X1 ? 1 : 2);
@@ -220,8 +283,7 @@ int enqueue_chunk(bd_engine* e, const float* x, int64_t n, int hop_frames, float
         const int nb = static_cast<int>(std::min<int64_t>(e->S2, P - big));
         // ---------------- frontend: log-mel of the whole late batch in one launch (24.6 KB per patch)
         {
-            const int n_fr = (nb - 1) * hop_frames + kPatchFrames;
-            BD_CHECK(e, launch_logmel(x, n, big * hop_frames, n_fr, e->d_tab, e->d_logmel, e->num_sms, st));
+            if (run_frontend(e, job, big, nb, hop_frames, st)) return 1;
             mark(e, CAT_FRONTEND, st);
             if (stop_at(0, e->d_logmel, false, 0)) return 0;
         }
@@ -307,9 +369,13 @@ int enqueue_chunk(bd_engine* e, const float* x, int64_t n, int hop_frames, float
 }
 
 // Run (or replay) the chunk on s_compute.
-int run_chunk(bd_engine* e, const float* x, int64_t n, int hop_frames, float* d_act, float* d_emb, int64_t P) {
+int run_chunk(bd_engine* e, const float* x, int64_t n, int hop_frames, float* d_act, float* d_emb, int64_t P,
+              bool allow_graph = true) {
     if (P <= 0) return 0;
-    if (!e->use_graph || e->profiling) return enqueue_chunk(e, x, n, hop_frames, d_act, d_emb, P, e->s_compute);
+    FrontJob job;
+    job.x = x;
+    job.n = n;
+    if (!e->use_graph || e->profiling || !allow_graph) return enqueue_chunk(e, job, hop_frames, d_act, d_emb, P, e->s_compute);
     GraphKey key{x, n, hop_frames, d_act, d_emb};
     auto it = e->graphs.find(key);
     if (it == e->graphs.end()) {
@@ -320,7 +386,7 @@ int run_chunk(bd_engine* e, const float* x, int64_t n, int hop_frames, float* d_
         }
         const int64_t before = e->launch_count;
         BD_CHECK(e, cudaStreamBeginCapture(e->s_compute, cudaStreamCaptureModeThreadLocal));
-        const int rc = enqueue_chunk(e, x, n, hop_frames, d_act, d_emb, P, e->s_compute);
+        const int rc = enqueue_chunk(e, job, hop_frames, d_act, d_emb, P, e->s_compute);
         cudaGraph_t g = nullptr;
         cudaError_t ce = cudaStreamEndCapture(e->s_compute, &g);
         const int64_t per_graph = e->launch_count - before;
@@ -343,6 +409,7 @@ int ensure_slot(bd_engine* e, Slot& s, int64_t n, int64_t P) {
     if (n > s.in_cap) {
         if (s.d_in) cudaFree(s.d_in);
         s.d_in = nullptr;
+        s.in_cap = 0;
         const int64_t cap = ((n + 4095) / 4096) * 4096 + 64;
         BD_CHECK(e, cudaMalloc(&s.d_in, cap * sizeof(float)));
         s.in_cap = cap;
@@ -351,11 +418,167 @@ int ensure_slot(bd_engine* e, Slot& s, int64_t n, int64_t P) {
         if (s.d_act) cudaFree(s.d_act);
         if (s.d_emb) cudaFree(s.d_emb);
         s.d_act = s.d_emb = nullptr;
+        s.out_cap = 0;
         const int64_t cap = ((P + 255) / 256) * 256;
         BD_CHECK(e, cudaMalloc(&s.d_act, cap * e->n_classes * sizeof(float)));
         BD_CHECK(e, cudaMalloc(&s.d_emb, cap * kEmb * sizeof(float)));
         s.out_cap = cap;
     }
+    return 0;
+}
+
+bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// pinned staging for the results of a slot (grown on demand)
+int ensure_staging(bd_engine* e, Slot& s, int64_t act_floats, int64_t emb_floats) {
+    if (act_floats > s.h_act_cap) {
+        if (s.h_act) cudaFreeHost(s.h_act);
+        s.h_act = nullptr; s.h_act_cap = 0;
+        const int64_t cap = ((act_floats + 4095) / 4096) * 4096;
+        BD_CHECK(e, cudaHostAlloc(reinterpret_cast<void**>(&s.h_act), cap * sizeof(float), cudaHostAllocDefault));
+        s.h_act_cap = cap;
+    }
+    if (emb_floats > s.h_emb_cap) {
+        if (s.h_emb) cudaFreeHost(s.h_emb);
+        s.h_emb = nullptr; s.h_emb_cap = 0;
+        const int64_t cap = ((emb_floats + 65535) / 65536) * 65536;
+        BD_CHECK(e, cudaHostAlloc(reinterpret_cast<void**>(&s.h_emb), cap * sizeof(float), cudaHostAllocDefault));
+        s.h_emb_cap = cap;
+    }
+    return 0;
+}
+
+// Where the device->host copies of a slot go: straight to the caller's buffer when that is pinned, else to the slot's
+// pinned staging (bd_wait then finishes with a host memcpy).
+int route_outputs(bd_engine* e, Slot& s, float* act, float* emb) {
+    const int64_t na = s.P * e->n_classes, ne = emb ? s.P * kEmb : 0;
+    const bool act_direct = is_pinned_host(act), emb_direct = emb == nullptr || is_pinned_host(emb);
+    if (ensure_staging(e, s, act_direct ? 0 : na, emb_direct ? 0 : ne)) return 1;
+    s.user_act = act_direct ? nullptr : act;
+    s.user_emb = emb_direct ? nullptr : emb;
+    s.dst_act = act_direct ? act : s.h_act;
+    s.dst_emb = emb == nullptr ? nullptr : (emb_direct ? emb : s.h_emb);
+    return 0;
+}
+
+struct SlotOut { float* act; float* emb; };
+
+// ---- launching what is pending ------------------------------------------------------------------------------------
+// One chunk alone: the chunk pipeline as before (CUDA graph for long chunks).  Several chunks: ONE pass of the CNN over
+// all of them (a 208-patch chunk on its own leaves most of the 148 persistent CTAs of every kernel idle).
+int launch_group(bd_engine* e, const std::vector<int>& group, const std::vector<SlotOut>& outs) {
+    const int hop = e->slots[group[0]].hop;
+    for (int si : group) BD_CHECK(e, cudaStreamWaitEvent(e->s_compute, e->slots[si].ev_in, 0));
+    if (group.size() == 1) {
+        Slot& s = e->slots[group[0]];
+        if (run_chunk(e, s.d_in, s.n, hop, s.d_act, s.want_emb ? s.d_emb : nullptr, s.P, s.P >= 512)) return 1;
+        BD_CHECK(e, cudaEventRecord(s.ev_comp, e->s_compute));
+        BD_CHECK(e, cudaEventRecord(e->ev_last_comp, e->s_compute));
+        BD_CHECK(e, cudaStreamWaitEvent(e->s_out, s.ev_comp, 0));
+        BD_CHECK(e, cudaMemcpyAsync(outs[0].act, s.d_act, s.P * e->n_classes * sizeof(float), cudaMemcpyDeviceToHost, e->s_out));
+        if (s.want_emb)
+            BD_CHECK(e, cudaMemcpyAsync(outs[0].emb, s.d_emb, s.P * kEmb * sizeof(float), cudaMemcpyDeviceToHost, e->s_out));
+        BD_CHECK(e, cudaEventRecord(s.ev_out, e->s_out));
+        e->batches++; e->batched_chunks++;
+        return 0;
+    }
+    FrontJob job;
+    const int tail_slots = (kPatchFrames + hop - 1) / hop - 1;      // slots between two chunks (0 at hop 96, 1 at hop 48)
+    int64_t g = 0;
+    bool any_emb = false;
+    std::vector<int64_t> g0(group.size());
+    for (size_t i = 0; i < group.size(); ++i) {
+        Slot& s = e->slots[group[i]];
+        const bool last = i + 1 == group.size();
+        g0[i] = g;
+        LogmelSeg& sg = job.segs[job.n_segs++];
+        sg.x = s.d_in;
+        sg.n_valid = s.n;
+        sg.frame_begin = 0;
+        sg.row_begin = static_cast<int>(g * hop);
+        const int64_t g_next = g + s.P + tail_slots;
+        sg.n_rows = static_cast<int>(last ? (s.P - 1) * hop + kPatchFrames : (g_next - g) * hop);
+        g = last ? g + s.P : g_next;
+        any_emb = any_emb || s.want_emb;
+    }
+    const int64_t P_total = g;
+    if (P_total > e->S2) return fail(e, "internal: coalesced batch larger than one late batch");
+    const int set = e->batch_set;
+    e->batch_set ^= 1;
+    if (!e->d_act_batch[set]) BD_CHECK(e, cudaMalloc(&e->d_act_batch[set], static_cast<size_t>(e->S2) * e->n_classes * sizeof(float)));
+    if (any_emb && !e->d_emb_batch[set]) BD_CHECK(e, cudaMalloc(&e->d_emb_batch[set], static_cast<size_t>(e->S2) * kEmb * sizeof(float)));
+    BD_CHECK(e, cudaStreamWaitEvent(e->s_compute, e->ev_batch_out[set], 0));   // the set's previous results have left
+    if (enqueue_chunk(e, job, hop, e->d_act_batch[set], any_emb ? e->d_emb_batch[set] : nullptr, P_total, e->s_compute))
+        return 1;
+    Slot& s0 = e->slots[group[0]];
+    BD_CHECK(e, cudaEventRecord(s0.ev_comp, e->s_compute));
+    BD_CHECK(e, cudaEventRecord(e->ev_last_comp, e->s_compute));
+    BD_CHECK(e, cudaStreamWaitEvent(e->s_out, s0.ev_comp, 0));
+    for (size_t i = 0; i < group.size(); ++i) {
+        Slot& s = e->slots[group[i]];
+        BD_CHECK(e, cudaMemcpyAsync(outs[i].act, e->d_act_batch[set] + g0[i] * e->n_classes,
+                                    s.P * e->n_classes * sizeof(float), cudaMemcpyDeviceToHost, e->s_out));
+        if (s.want_emb)
+            BD_CHECK(e, cudaMemcpyAsync(outs[i].emb, e->d_emb_batch[set] + g0[i] * kEmb, s.P * kEmb * sizeof(float),
+                                        cudaMemcpyDeviceToHost, e->s_out));
+        BD_CHECK(e, cudaEventRecord(s.ev_out, e->s_out));
+    }
+    BD_CHECK(e, cudaEventRecord(e->ev_batch_out[set], e->s_out));
+    e->batches++; e->batched_chunks += static_cast<int64_t>(group.size());
+    return 0;
+}
+
+// Launch everything that is pending, grouped into batches of chunks with the same hop that fit one late batch.
+// Caller holds e->mu.  On failure the affected slots are released (state 0) so the engine stays usable.
+int flush_pending(bd_engine* e) {
+    size_t pos = 0;
+    int rc = 0;
+    while (pos < e->pending.size() && rc == 0) {
+        std::vector<int> group;
+        std::vector<SlotOut> outs;
+        const int hop = e->slots[e->pending[pos]].hop;
+        const int tail_slots = (kPatchFrames + hop - 1) / hop - 1;
+        int64_t g = 0;
+        while (pos < e->pending.size() && static_cast<int>(group.size()) < kMaxLogmelSegs) {
+            Slot& s = e->slots[e->pending[pos]];
+            if (s.hop != hop) break;
+            if (!group.empty() && g + tail_slots + s.P > e->S2) break;
+            g += (group.empty() ? 0 : tail_slots) + s.P;
+            group.push_back(e->pending[pos]);
+            outs.push_back(SlotOut{s.dst_act, s.want_emb ? s.dst_emb : nullptr});
+            ++pos;
+            if (g >= e->S2) break;
+        }
+        rc = launch_group(e, group, outs);
+        for (int si : group) e->slots[si].state = rc == 0 ? 2 : 0;
+    }
+    if (rc != 0)
+        for (; pos < e->pending.size(); ++pos) e->slots[e->pending[pos]].state = 0;
+    else
+        e->any_launched = true;
+    e->pending.clear();
+    return rc;
+}
+
+bool gpu_idle(bd_engine* e) {
+    if (!e->any_launched) return true;
+    const cudaError_t q = cudaEventQuery(e->ev_last_comp);
+    if (q == cudaErrorNotReady) { cudaGetLastError(); return false; }
+    return true;
+}
+
+// After a chunk has been queued: launch now when the GPU has nothing to do (latency) or when a full batch is waiting;
+// otherwise let chunks accumulate behind the running batch (throughput: they will run as ONE pass).
+int maybe_flush(bd_engine* e) {
+    int64_t patches = 0;
+    for (int si : e->pending) patches += e->slots[si].P;
+    if (!e->auto_flush) return 0;
+    if (patches >= e->coalesce_target || static_cast<int>(e->pending.size()) >= kMaxLogmelSegs || gpu_idle(e))
+        return flush_pending(e);
     return 0;
 }
 
@@ -407,8 +630,15 @@ void bd_engine_destroy(bd_engine* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(e->d_act_batch[i]); cudaFree(e->d_emb_batch[i]);
+        if (e->ev_batch_out[i]) cudaEventDestroy(e->ev_batch_out[i]);
+    }
+    if (e->ev_last_comp) cudaEventDestroy(e->ev_last_comp);
     for (auto& s : e->slots) {
         cudaFree(s.d_in); cudaFree(s.d_pcm); cudaFree(s.d_act); cudaFree(s.d_emb);
+        if (s.h_act) cudaFreeHost(s.h_act);
+        if (s.h_emb) cudaFreeHost(s.h_emb);
         if (s.ev_in) cudaEventDestroy(s.ev_in);
         if (s.ev_comp) cudaEventDestroy(s.ev_comp);
         if (s.ev_out) cudaEventDestroy(s.ev_out);
@@ -469,6 +699,11 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
     BD_CREATE(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
     BD_CREATE(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
     BD_CREATE(frontend_init_device());
+    BD_CREATE(frontend2_init_device());
+    {
+        const char* v1 = getenv("BD_FRONTEND_V1");
+        e->frontend_v1 = v1 && atoi(v1) != 0;
+    }
     BD_CREATE(layers_init_device());
     if (e->precision != BD_PRECISION_FP32_SIMT) BD_CREATE(pw_gemm_init_device());
     if (e->precision != BD_PRECISION_FP32_SIMT) BD_CREATE(sep_fused3_init_device());
@@ -501,6 +736,7 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
             for (int j = 0; j < len; ++j) t.mel_w[off + j] = w->mel[(first + j) * kMel + m];
             off += len;
         }
+        frontend2_build_mel(t, &e->mel_param);
         BD_CREATE(cudaMalloc(&e->d_tab, sizeof(FrontendTables)));
         BD_CREATE(cudaMemcpy(e->d_tab, &t, sizeof(t), cudaMemcpyHostToDevice));
     }
@@ -599,8 +835,12 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
     }
 
     // ---- host-chunk slots
-    int ns = cfg->n_slots <= 0 ? 2 : std::min(cfg->n_slots, 4);
+    int ns = cfg->n_slots <= 0 ? 2 : std::min(cfg->n_slots, 64);
     e->slots.resize(ns);
+    for (int i = 0; i < 2; ++i) BD_CREATE(cudaEventCreateWithFlags(&e->ev_batch_out[i], cudaEventDisableTiming));
+    BD_CREATE(cudaEventCreateWithFlags(&e->ev_last_comp, cudaEventDisableTiming));
+    e->coalesce_target = std::max<int64_t>(1, static_cast<int64_t>(e->S2) * 3 / 4);
+    if (const char* ct = getenv("BD_COALESCE_PATCHES")) e->coalesce_target = std::max<int64_t>(1, atoll(ct));
     for (auto& s : e->slots) {
         BD_CREATE(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
         BD_CREATE(cudaEventCreateWithFlags(&s.ev_comp, cudaEventDisableTiming));
@@ -612,9 +852,20 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
     return 0;
 }
 
+int32_t bd_flush(bd_engine* e) {
+    if (!e) return 1;
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
+    BD_CHECK(e, cudaSetDevice(e->device));
+    return flush_pending(e);
+}
+
 int32_t bd_synchronize(bd_engine* e) {
     if (!e) return 1;
-    BD_CHECK(e, cudaSetDevice(e->device));
+    {
+        std::lock_guard<std::recursive_mutex> lk(e->mu);
+        BD_CHECK(e, cudaSetDevice(e->device));
+        if (flush_pending(e)) return 1;
+    }
     BD_CHECK(e, cudaStreamSynchronize(e->s_in));
     BD_CHECK(e, cudaStreamSynchronize(e->s_compute));
     BD_CHECK(e, cudaStreamSynchronize(e->s_out));
@@ -624,6 +875,7 @@ int32_t bd_synchronize(bd_engine* e) {
 int32_t bd_predict_device(bd_engine* e, const float* d_samples, int64_t n, int32_t hop_frames, float* d_act,
                           float* d_emb, int64_t* n_patches) {
     if (!e) return 1;
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     if (n < 0 || hop_frames < 1 || hop_frames > kPatchFrames) return fail(e, "bad n / hop_frames");
     BD_CHECK(e, cudaSetDevice(e->device));
     int64_t P = 0;
@@ -638,38 +890,70 @@ int32_t bd_predict_device(bd_engine* e, const float* d_samples, int64_t n, int32
 int32_t bd_submit_host(bd_engine* e, int32_t slot, const float* samples, int64_t n, int32_t hop_frames, float* act,
                        float* emb, int64_t* n_patches) {
     if (!e) return 1;
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     if (slot < 0 || slot >= static_cast<int>(e->slots.size())) return fail(e, "slot out of range");
     if (n < 0 || hop_frames < 1 || hop_frames > kPatchFrames) return fail(e, "bad n / hop_frames");
     BD_CHECK(e, cudaSetDevice(e->device));
     Slot& s = e->slots[slot];
-    if (s.busy) return fail(e, "slot still in flight: call bd_wait first");
+    if (s.state != 0) return fail(e, "slot still in flight: call bd_wait first");
     int64_t P = 0;
     frames_for(n, hop_frames, nullptr, nullptr, &P);
     if (n_patches) *n_patches = P;
     if (P == 0) return 0;
     if (!samples || !act) return fail(e, "null host buffer");
     if (ensure_slot(e, s, n, P)) return 1;
+    s.n = n; s.P = P; s.hop = hop_frames; s.want_emb = emb != nullptr;
+    if (route_outputs(e, s, act, emb)) return 1;
     BD_CHECK(e, cudaMemcpyAsync(s.d_in, samples, n * sizeof(float), cudaMemcpyHostToDevice, e->s_in));
     BD_CHECK(e, cudaEventRecord(s.ev_in, e->s_in));
-    BD_CHECK(e, cudaStreamWaitEvent(e->s_compute, s.ev_in, 0));
-    if (run_chunk(e, s.d_in, n, hop_frames, s.d_act, emb ? s.d_emb : nullptr, P)) return 1;
-    BD_CHECK(e, cudaEventRecord(s.ev_comp, e->s_compute));
-    BD_CHECK(e, cudaStreamWaitEvent(e->s_out, s.ev_comp, 0));
-    BD_CHECK(e, cudaMemcpyAsync(act, s.d_act, P * e->n_classes * sizeof(float), cudaMemcpyDeviceToHost, e->s_out));
-    if (emb) BD_CHECK(e, cudaMemcpyAsync(emb, s.d_emb, P * kEmb * sizeof(float), cudaMemcpyDeviceToHost, e->s_out));
-    BD_CHECK(e, cudaEventRecord(s.ev_out, e->s_out));
-    s.busy = true;
-    return 0;
+    s.state = 1;
+    e->pending.push_back(slot);
+    return maybe_flush(e);
 }
 
 int32_t bd_wait(bd_engine* e, int32_t slot) {
     if (!e) return 1;
-    if (slot < 0 || slot >= static_cast<int>(e->slots.size())) return fail(e, "slot out of range");
+    cudaEvent_t ev = nullptr;
+    {
+        std::lock_guard<std::recursive_mutex> lk(e->mu);
+        if (slot < 0 || slot >= static_cast<int>(e->slots.size())) return fail(e, "slot out of range");
+        Slot& s = e->slots[slot];
+        if (s.state == 0) return 0;
+        BD_CHECK(e, cudaSetDevice(e->device));
+        if (s.state == 1 && flush_pending(e)) return 1;
+        if (s.state != 2) return fail(e, "slot was released by a failed launch");
+        ev = s.ev_out;
+    }
+    const cudaError_t we = cudaEventSynchronize(ev);        // outside the lock: the other thread keeps submitting
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     Slot& s = e->slots[slot];
-    if (!s.busy) return 0;
-    BD_CHECK(e, cudaSetDevice(e->device));
-    s.busy = false;
-    BD_CHECK(e, cudaEventSynchronize(s.ev_out));
+    s.state = 0;
+    BD_CHECK(e, we);
+    if (s.user_act) std::memcpy(s.user_act, s.h_act, static_cast<size_t>(s.P) * e->n_classes * sizeof(float));
+    if (s.user_emb) std::memcpy(s.user_emb, s.h_emb, static_cast<size_t>(s.P) * kEmb * sizeof(float));
+    s.user_act = s.user_emb = nullptr;
+    return 0;
+}
+
+int32_t bd_set_auto_flush(bd_engine* e, int32_t on) {
+    if (!e) return 1;
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
+    e->auto_flush = on != 0;
+    return 0;
+}
+
+int32_t bd_slot_state(bd_engine* e, int32_t slot) {
+    if (!e) return -1;
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
+    if (slot < 0 || slot >= static_cast<int>(e->slots.size())) return -1;
+    return e->slots[slot].state;
+}
+
+int32_t bd_batch_stats(bd_engine* e, int64_t* batches, int64_t* chunks) {
+    if (!e) return 1;
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
+    if (batches) *batches = e->batches;
+    if (chunks) *chunks = e->batched_chunks;
     return 0;
 }
 
@@ -681,9 +965,29 @@ int32_t bd_predict_host(bd_engine* e, const float* samples, int64_t n, int32_t h
     return bd_wait(e, 0);
 }
 
+/* pinned (page-locked) host memory for the streamer's chunk ring and for result buffers: DMA reads / writes it
+ * directly, so bd_submit_* returns as soon as the copies are queued */
+int32_t bd_host_alloc(size_t bytes, int32_t write_combined, void** out) {
+    if (!out) return 1;
+    *out = nullptr;
+    unsigned flags = cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0u);
+    const cudaError_t ce = cudaHostAlloc(out, bytes ? bytes : 1, flags);
+    if (ce != cudaSuccess) {
+        g_create_error = std::string("cudaHostAlloc: ") + cudaGetErrorString(ce);
+        *out = nullptr;
+        return 1;
+    }
+    return 0;
+}
+
+void bd_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 int32_t bd_profile_device(bd_engine* e, const float* d_samples, int64_t n, int32_t hop_frames, float* ms,
                           int64_t* launches) {
     if (!e) return 1;
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     if (n < 0 || hop_frames < 1 || hop_frames > kPatchFrames) return fail(e, "bad n / hop_frames");
     BD_CHECK(e, cudaSetDevice(e->device));
     int64_t P = 0;
@@ -700,7 +1004,10 @@ int32_t bd_profile_device(bd_engine* e, const float* d_samples, int64_t n, int32
     cudaEventCreate(&start);
     cudaEventRecord(start, e->s_compute);
     const int64_t before = e->launch_count;
-    const int rc = enqueue_chunk(e, d_samples, n, hop_frames, d_act, nullptr, P, e->s_compute);
+    FrontJob pjob;
+    pjob.x = d_samples;
+    pjob.n = n;
+    const int rc = enqueue_chunk(e, pjob, hop_frames, d_act, nullptr, P, e->s_compute);
     e->profiling = false;
     e->launch_count = before;
     cudaError_t se = cudaStreamSynchronize(e->s_compute);
@@ -726,6 +1033,7 @@ int32_t bd_profile_device(bd_engine* e, const float* d_samples, int64_t n, int32
 int32_t bd_bench_device(bd_engine* e, const float* d_samples, int64_t n, int32_t hop_frames, float* d_act,
                         int32_t steps, float* ms_total) {
     if (!e) return 1;
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     if (n < 0 || hop_frames < 1 || hop_frames > kPatchFrames || steps < 1) return fail(e, "bad arguments");
     BD_CHECK(e, cudaSetDevice(e->device));
     int64_t P = 0;
@@ -840,6 +1148,7 @@ static int run_resample(bd_engine* e, const bd_engine::Resampler* r, const void*
 int32_t bd_resample_device(bd_engine* e, const void* d_in, int32_t fmt, int32_t channels, int64_t n_frames,
                            int32_t src_rate, float* d_out, int64_t out_capacity, int64_t* n_out) {
     if (!e) return 1;
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     if ((fmt != 0 && fmt != 1) || channels < 1 || channels > 8 || src_rate < 1000 || n_frames < 0)
         return fail(e, "bad resample arguments");
     BD_CHECK(e, cudaSetDevice(e->device));
@@ -859,13 +1168,14 @@ int32_t bd_submit_pcm_host(bd_engine* e, int32_t slot, const void* pcm, int32_t 
                            int64_t n_frames, int32_t src_rate, int32_t hop_frames, float* act, float* emb,
                            int64_t* n_patches) {
     if (!e) return 1;
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     if (slot < 0 || slot >= static_cast<int>(e->slots.size())) return fail(e, "slot out of range");
     if ((fmt != 0 && fmt != 1) || channels < 1 || channels > 8 || src_rate < 1000 || n_frames < 0)
         return fail(e, "bad PCM arguments");
     if (hop_frames < 1 || hop_frames > kPatchFrames) return fail(e, "bad hop_frames");
     BD_CHECK(e, cudaSetDevice(e->device));
     Slot& s = e->slots[slot];
-    if (s.busy) return fail(e, "slot still in flight: call bd_wait first");
+    if (s.state != 0) return fail(e, "slot still in flight: call bd_wait first");
     const int64_t n = bd_resample_out_len(n_frames, src_rate);
     int64_t P = 0;
     frames_for(n, hop_frames, nullptr, nullptr, &P);
@@ -877,6 +1187,7 @@ int32_t bd_submit_pcm_host(bd_engine* e, int32_t slot, const void* pcm, int32_t 
     if (pcm_bytes > s.pcm_cap) {
         if (s.d_pcm) cudaFree(s.d_pcm);
         s.d_pcm = nullptr;
+        s.pcm_cap = 0;
         const int64_t cap = ((pcm_bytes + 65535) / 65536) * 65536;
         BD_CHECK(e, cudaMalloc(&s.d_pcm, cap));
         s.pcm_cap = cap;
@@ -884,23 +1195,24 @@ int32_t bd_submit_pcm_host(bd_engine* e, int32_t slot, const void* pcm, int32_t 
     bd_engine::Resampler ident{1, 1, 1, nullptr};
     bd_engine::Resampler* r = &ident;
     if (src_rate != 16000 && get_resampler(e, src_rate, &r)) return 1;
+    s.n = n; s.P = P; s.hop = hop_frames; s.want_emb = emb != nullptr;
+    if (route_outputs(e, s, act, emb)) return 1;
     if (n_frames > 0) BD_CHECK(e, cudaMemcpyAsync(s.d_pcm, pcm, pcm_bytes, cudaMemcpyHostToDevice, e->s_in));
     BD_CHECK(e, cudaEventRecord(s.ev_in, e->s_in));
+    // downmix + resample to the slot's 16 kHz buffer right away (stream order: behind whatever batch is running); the
+    // CNN pass itself is launched with the other pending chunks
     BD_CHECK(e, cudaStreamWaitEvent(e->s_compute, s.ev_in, 0));
     if (run_resample(e, r, s.d_pcm, fmt, channels, n_frames, s.d_in, n, e->s_compute)) return 1;
-    if (run_chunk(e, s.d_in, n, hop_frames, s.d_act, emb ? s.d_emb : nullptr, P)) return 1;
-    BD_CHECK(e, cudaEventRecord(s.ev_comp, e->s_compute));
-    BD_CHECK(e, cudaStreamWaitEvent(e->s_out, s.ev_comp, 0));
-    BD_CHECK(e, cudaMemcpyAsync(act, s.d_act, P * e->n_classes * sizeof(float), cudaMemcpyDeviceToHost, e->s_out));
-    if (emb) BD_CHECK(e, cudaMemcpyAsync(emb, s.d_emb, P * kEmb * sizeof(float), cudaMemcpyDeviceToHost, e->s_out));
-    BD_CHECK(e, cudaEventRecord(s.ev_out, e->s_out));
-    s.busy = true;
-    return 0;
+    BD_CHECK(e, cudaEventRecord(s.ev_in, e->s_compute));
+    s.state = 1;
+    e->pending.push_back(slot);
+    return maybe_flush(e);
 }
 
 int32_t bd_resample_host(bd_engine* e, const void* in, int32_t fmt, int32_t channels, int64_t n_frames,
                          int32_t src_rate, float* out, int64_t out_capacity, int64_t* n_out) {
     if (!e) return 1;
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     if ((fmt != 0 && fmt != 1) || channels < 1 || channels > 8 || src_rate < 1000 || n_frames < 0)
         return fail(e, "bad resample arguments");
     BD_CHECK(e, cudaSetDevice(e->device));
@@ -930,13 +1242,19 @@ int32_t bd_resample_host(bd_engine* e, const void* in, int32_t fmt, int32_t chan
 // ------------------------------------------------------------------------------------------ test hooks
 int32_t bd_debug_logmel(bd_engine* e, const float* samples, int64_t n, int64_t n_frames, float* logmel) {
     if (!e) return 1;
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     BD_CHECK(e, cudaSetDevice(e->device));
     if (n_frames <= 0) return 0;
     float *d_x = nullptr, *d_lm = nullptr;
     BD_CHECK(e, cudaMalloc(&d_x, std::max<int64_t>(n, 1) * sizeof(float)));
     BD_CHECK(e, cudaMalloc(&d_lm, n_frames * kMel * sizeof(float)));
     BD_CHECK(e, cudaMemcpyAsync(d_x, samples, n * sizeof(float), cudaMemcpyHostToDevice, e->s_compute));
-    BD_CHECK(e, launch_logmel(d_x, n, 0, static_cast<int>(n_frames), e->d_tab, d_lm, e->num_sms, e->s_compute));
+    if (e->frontend_v1) {
+        BD_CHECK(e, launch_logmel(d_x, n, 0, static_cast<int>(n_frames), e->d_tab, d_lm, e->num_sms, e->s_compute));
+    } else {
+        LogmelSeg sg{d_x, n, 0, 0, static_cast<int>(n_frames)};
+        BD_CHECK(e, launch_logmel_segs(&sg, 1, e->mel_param, e->d_tab->window, d_lm, n_frames, e->num_sms, e->s_compute));
+    }
     e->launch_count++;
     BD_CHECK(e, cudaStreamSynchronize(e->s_compute));
     BD_CHECK(e, cudaMemcpy(logmel, d_lm, n_frames * kMel * sizeof(float), cudaMemcpyDeviceToHost));
@@ -948,6 +1266,7 @@ int32_t bd_debug_logmel(bd_engine* e, const float* samples, int64_t n, int64_t n
 int32_t bd_debug_pw_gemm(bd_engine* e, const float* A, const float* W, const float* bias, int32_t M, int32_t N,
                          int32_t K, int32_t precision, int32_t block_n, float* C) {
     if (!e) return 1;
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     BD_CHECK(e, cudaSetDevice(e->device));
     const size_t na = static_cast<size_t>(M) * K, nw = static_cast<size_t>(N) * K, nc = static_cast<size_t>(M) * N;
     float *dA = nullptr, *dW = nullptr, *dB = nullptr, *dC = nullptr;
@@ -1007,6 +1326,7 @@ int32_t bd_debug_pw_gemm(bd_engine* e, const float* A, const float* W, const flo
 int32_t bd_debug_stage(bd_engine* e, const float* samples, int64_t n, int32_t hop_frames, int32_t stage, float* out,
                        int64_t out_capacity, int64_t* n_out) {
     if (!e) return 1;
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     if (stage < 0 || stage > 2 * (BD_N_LAYERS - 1) + 1) return fail(e, "stage out of range");
     if (n < 0 || hop_frames < 1 || hop_frames > kPatchFrames) return fail(e, "bad n / hop_frames");
     BD_CHECK(e, cudaSetDevice(e->device));
@@ -1021,7 +1341,10 @@ int32_t bd_debug_stage(bd_engine* e, const float* samples, int64_t n, int32_t ho
     BD_CHECK(e, cudaMalloc(&d_act, P * e->n_classes * sizeof(float)));
     BD_CHECK(e, cudaMemcpyAsync(d_x, samples, n * sizeof(float), cudaMemcpyHostToDevice, e->s_compute));
     e->dbg_ptr = nullptr;
-    int rc = enqueue_chunk(e, d_x, n, hop_frames, d_act, nullptr, P, e->s_compute, stage);
+    FrontJob djob;
+    djob.x = d_x;
+    djob.n = n;
+    int rc = enqueue_chunk(e, djob, hop_frames, d_act, nullptr, P, e->s_compute, stage);
     if (rc == 0) {
         cudaError_t se = cudaStreamSynchronize(e->s_compute);
         if (se != cudaSuccess) rc = fail(e, std::string("stage execution: ") + cudaGetErrorString(se));

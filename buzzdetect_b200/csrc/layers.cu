@@ -8,6 +8,7 @@
 // Layout: NHWC, H = time, W = mel; activations are [P*H*W, C] row-major so a pointwise conv is a plain GEMM.
 #include <cstdlib>
 
+#include "bd_common.cuh"
 #include "bd_kernels.cuh"
 
 namespace bd {
@@ -167,15 +168,15 @@ __global__ void __launch_bounds__(256) conv1_dw2_kernel(const float* __restrict_
                 if (OUT_MODE == 0) {
                     *reinterpret_cast<float4*>(out_f32 + o) = a;
                 } else {
-                    const __half h0 = __float2half_rn(a.x), h1 = __float2half_rn(a.y);
-                    const __half h2 = __float2half_rn(a.z), h3 = __float2half_rn(a.w);
+                    const __half h0 = half_sat(a.x), h1 = half_sat(a.y);
+                    const __half h2 = half_sat(a.z), h3 = half_sat(a.w);
                     __half2 hp[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
                     *reinterpret_cast<uint2*>(out_hi + o) = *reinterpret_cast<uint2*>(hp);
                     if (OUT_MODE == 2) {
-                        __half2 lp[2] = {__halves2half2(__float2half_rn(a.x - __half2float(h0)),
-                                                        __float2half_rn(a.y - __half2float(h1))),
-                                         __halves2half2(__float2half_rn(a.z - __half2float(h2)),
-                                                        __float2half_rn(a.w - __half2float(h3)))};
+                        __half2 lp[2] = {__halves2half2(half_sat(a.x - __half2float(h0)),
+                                                        half_sat(a.y - __half2float(h1))),
+                                         __halves2half2(half_sat(a.z - __half2float(h2)),
+                                                        half_sat(a.w - __half2float(h3)))};
                         *reinterpret_cast<uint2*>(out_lo + o) = *reinterpret_cast<uint2*>(lp);
                     }
                 }
@@ -255,14 +256,14 @@ __global__ void __launch_bounds__(256) depthwise_kernel(const float* __restrict_
             if (OUT_MODE == 0) {
                 *reinterpret_cast<float4*>(out_f32 + o) = a;
             } else {
-                const __half h0 = __float2half_rn(a.x), h1 = __float2half_rn(a.y);
-                const __half h2 = __float2half_rn(a.z), h3 = __float2half_rn(a.w);
+                const __half h0 = half_sat(a.x), h1 = half_sat(a.y);
+                const __half h2 = half_sat(a.z), h3 = half_sat(a.w);
                 __half2 hp[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
                 *reinterpret_cast<uint2*>(out_hi + o) = *reinterpret_cast<uint2*>(hp);
                 if (OUT_MODE == 2) {
                     __half2 lp[2] = {
-                        __halves2half2(__float2half_rn(a.x - __half2float(h0)), __float2half_rn(a.y - __half2float(h1))),
-                        __halves2half2(__float2half_rn(a.z - __half2float(h2)), __float2half_rn(a.w - __half2float(h3)))};
+                        __halves2half2(half_sat(a.x - __half2float(h0)), half_sat(a.y - __half2float(h1))),
+                        __halves2half2(half_sat(a.z - __half2float(h2)), half_sat(a.w - __half2float(h3)))};
                     *reinterpret_cast<uint2*>(out_lo + o) = *reinterpret_cast<uint2*>(lp);
                 }
             }
@@ -348,14 +349,14 @@ __global__ void __launch_bounds__(256) depthwise2_kernel(const float* __restrict
                 if (OUT_MODE == 0) {
                     *reinterpret_cast<float4*>(out_f32 + oo) = a;
                 } else {
-                    const __half h0 = __float2half_rn(a.x), h1 = __float2half_rn(a.y);
-                    const __half h2 = __float2half_rn(a.z), h3 = __float2half_rn(a.w);
+                    const __half h0 = half_sat(a.x), h1 = half_sat(a.y);
+                    const __half h2 = half_sat(a.z), h3 = half_sat(a.w);
                     __half2 hp[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
                     *reinterpret_cast<uint2*>(out_hi + oo) = *reinterpret_cast<uint2*>(hp);
                     if (OUT_MODE == 2) {
                         __half2 lp[2] = {
-                            __halves2half2(__float2half_rn(a.x - __half2float(h0)), __float2half_rn(a.y - __half2float(h1))),
-                            __halves2half2(__float2half_rn(a.z - __half2float(h2)), __float2half_rn(a.w - __half2float(h3)))};
+                            __halves2half2(half_sat(a.x - __half2float(h0)), half_sat(a.y - __half2float(h1))),
+                            __halves2half2(half_sat(a.z - __half2float(h2)), half_sat(a.w - __half2float(h3)))};
                         *reinterpret_cast<uint2*>(out_lo + oo) = *reinterpret_cast<uint2*>(lp);
                     }
                 }

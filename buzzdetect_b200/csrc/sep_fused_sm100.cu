@@ -98,13 +98,13 @@ template <int NSPLIT>
 __device__ __forceinline__ void store_a(uint32_t a_hi, uint32_t a_lo, uint32_t row, uint32_t chunk, uint32_t half8, float4 a) {
     a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
     const uint32_t off = (row >> 3) * 1024u + (row & 7u) * 128u + ((chunk ^ (row & 7u)) << 4) + half8;
-    const __half h0 = __float2half_rn(a.x), h1 = __float2half_rn(a.y);
-    const __half h2 = __float2half_rn(a.z), h3 = __float2half_rn(a.w);
+    const __half h0 = half_sat(a.x), h1 = half_sat(a.y);
+    const __half h2 = half_sat(a.z), h3 = half_sat(a.w);
     __half2 hp[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
     sts64(a_hi + off, reinterpret_cast<uint32_t*>(hp)[0], reinterpret_cast<uint32_t*>(hp)[1]);
     if (NSPLIT > 1) {
-        __half2 lp[2] = {__halves2half2(__float2half_rn(a.x - __half2float(h0)), __float2half_rn(a.y - __half2float(h1))),
-                         __halves2half2(__float2half_rn(a.z - __half2float(h2)), __float2half_rn(a.w - __half2float(h3)))};
+        __half2 lp[2] = {__halves2half2(half_sat(a.x - __half2float(h0)), half_sat(a.y - __half2float(h1))),
+                         __halves2half2(half_sat(a.z - __half2float(h2)), half_sat(a.w - __half2float(h3)))};
         sts64(a_lo + off, reinterpret_cast<uint32_t*>(lp)[0], reinterpret_cast<uint32_t*>(lp)[1]);
     }
 }

@@ -30,10 +30,11 @@ class YamnetK2(BaseEmbedder):
         from buzzdetect_b200 import capi
         self.hop_frames = capi.hop_frames_for(self.framehop_prop)
         if engine is None:
-            engine = capi.Engine(device=int(os.environ.get("BUZZ_B200_DEVICE", "0")), embedder=self._mel_variant)
+            engine = capi.Engine(device=int(os.environ.get("BUZZ_B200_DEVICE", "0")), embedder=self._mel_variant,
+                                 n_slots=int(os.environ.get("BUZZ_B200_SLOTS", "32")))
         self.model = engine
 
     def embed(self, audiosamples):
         from buzzdetect_b200.results import DeviceResults, as_host_f32
-        _, emb = self.model.predict(as_host_f32(audiosamples), self.hop_frames, want_embeddings=True)
-        return DeviceResults(emb)
+        tk = self.model.submit(as_host_f32(audiosamples), self.hop_frames, want_embeddings=True)
+        return DeviceResults(ticket=tk, which="emb")

@@ -2,36 +2,46 @@
 
 The reference stores a tf.Tensor in AssignChunk.results and the writer calls ``results.numpy()``
 (src/write/worker.py:69).  DeviceResults offers the same ``.numpy()`` (plus ``__array__``) over a host buffer that
-the CUDA stream has already finished writing, so it is safe to move to another thread."""
+the CUDA stream has finished writing by the time numpy() returns, so it is safe to move to another thread."""
 import numpy as np
 
 
 class DeviceResults:
-    __slots__ = ("_host", "embeddings")
+    """Results of one chunk.  Built either over a finished host array or over a capi.Ticket (chunk still in flight:
+    predict() has returned, the GPU may not have); numpy() / __array__ block until the activations are on the host."""
 
-    def __init__(self, host: np.ndarray, embeddings: np.ndarray | None = None):
+    __slots__ = ("_host", "_ticket", "_which", "embeddings")
+
+    def __init__(self, host=None, embeddings: np.ndarray | None = None, ticket=None, which: str = "act"):
         self._host = host
+        self._ticket = ticket
+        self._which = which
         self.embeddings = embeddings
 
     def numpy(self) -> np.ndarray:
+        if self._host is None:
+            tk = self._ticket.wait()
+            self._host = tk.act if self._which == "act" else tk.emb
+            self._ticket = None
         return self._host
 
     def __array__(self, dtype=None, copy=None):
-        return self._host if dtype is None else self._host.astype(dtype)
+        a = self.numpy()
+        return a if dtype is None else a.astype(dtype)
 
     def __getitem__(self, k):
-        return self._host[k]
+        return self.numpy()[k]
 
     def __len__(self):
-        return len(self._host)
+        return len(self.numpy())
 
     @property
     def shape(self):
-        return self._host.shape
+        return self.numpy().shape
 
     @property
     def dtype(self):
-        return self._host.dtype
+        return np.dtype(np.float32)
 
 
 def as_host_f32(samples) -> np.ndarray:

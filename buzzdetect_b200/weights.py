@@ -278,9 +278,24 @@ def pack_folded(layers: list[FoldedLayer]) -> tuple[np.ndarray, list[dict]]:
     return np.concatenate(chunks), meta
 
 
-def resolve_yamnet(verify: bool = True) -> tuple[dict, str]:
+def synthetic_allowed(flag: bool | None = None) -> bool:
+    """Synthetic YAMNet weights are an explicit opt-in: tests, bench.py and smoke() pass allow_synthetic=True or set
+    BUZZ_B200_ALLOW_SYNTHETIC=1.  A production run without the real blob must fail, not write detections from a random
+    network."""
+    if flag is not None:
+        return bool(flag)
+    return os.environ.get("BUZZ_B200_ALLOW_SYNTHETIC", "") not in ("", "0")
+
+
+def resolve_yamnet(verify: bool = True, allow_synthetic: bool | None = None) -> tuple[dict, str]:
     """(variables, provenance) -- provenance is 'real:<path>' or 'synthetic:<seed>'."""
     p = find_yamnet_blob()
     if p is not None:
         return load_yamnet_blob(p, verify=verify), f"real:{p}"
+    if not synthetic_allowed(allow_synthetic):
+        raise FileNotFoundError(
+            "YAMNet weights not found: set BUZZ_YAMNET_WEIGHTS to variables.data-00000-of-00001 (or run from a "
+            "buzzdetect checkout / set BUZZDETECT_ROOT).  The checkout this package was developed against ships only "
+            "variables.index (.MISSING_LARGE_BLOBS).  Seeded synthetic weights exist for tests and benchmarks only: "
+            "Engine(allow_synthetic=True) or BUZZ_B200_ALLOW_SYNTHETIC=1.")
     return synthetic_yamnet(), f"synthetic:{SYNTH_SEED}"

@@ -20,7 +20,14 @@
  *
  * Error model: functions return 0 on success, non-zero on failure; the message is kept per
  * engine (bd_last_error) -- the Python wrapper raises RuntimeError.  Nothing here aborts the process.
- * Threading: an engine is used by one thread at a time; different engines are independent (one per inferer thread).
+ * Threading: every entry point takes the engine's lock, so one thread may submit chunks (the inferer) while another
+ * waits for results (the writer); different engines are independent (one per inferer thread / GPU).
+ *
+ * Chunk coalescing: bd_submit_* queues the chunk's host->device copy at once but may defer its compute: when the GPU
+ * is idle the chunk is launched immediately, otherwise it waits and is launched TOGETHER with the chunks submitted
+ * behind it (one pass of the CNN over up to late_patches patches), because a 200 s chunk on its own cannot fill the
+ * GPU.  bd_wait / bd_flush / bd_synchronize launch whatever is still pending.  Results are identical either way: every
+ * chunk is framed and padded on its own (src/stream/worker.py:109-135 + features.py:82-108).
  */
 #ifndef BUZZDETECT_B200_H
 #define BUZZDETECT_B200_H
@@ -74,7 +81,7 @@ typedef struct bd_config {
     int32_t early_patches;         /* patches per sub-batch for frontend..layer 7 depthwise (0 = 4096)      */
     int32_t late_patches;          /* patches per sub-batch for layer 7 pointwise..head     (0 = 4096)      */
     int32_t use_graph;             /* 1 = capture and replay CUDA graphs per (n_samples, hop)               */
-    int32_t n_slots;               /* in-flight host chunks for bd_submit_host (1..4, 0 = 2)                */
+    int32_t n_slots;               /* in-flight host chunks for bd_submit_host (1..64, 0 = 2)               */
     int32_t fuse_mask;             /* bit (L-2): run separable layer L as ONE fused depthwise+pointwise kernel
                                       (ignored in BD_PRECISION_FP32_SIMT); BD_FUSE_CONV1_DW2: layer 1 + layer-2
                                       depthwise in one kernel; BD_FUSE_L12: layers 1+2 in one kernel.
@@ -107,7 +114,18 @@ int32_t bd_submit_pcm_host(bd_engine* e, int32_t slot, const void* pcm, int32_t 
                            int64_t n_frames, int32_t src_rate, int32_t hop_frames, float* act, float* emb,
                            int64_t* n_patches);
 int32_t bd_wait(bd_engine* e, int32_t slot);
+int32_t bd_flush(bd_engine* e);                  /* launch every pending chunk now (does not wait)                      */
 int32_t bd_synchronize(bd_engine* e);
+int32_t bd_set_auto_flush(bd_engine* e, int32_t on);   /* 0: submitted chunks wait for bd_wait / bd_flush (default 1) */
+int32_t bd_slot_state(bd_engine* e, int32_t slot);   /* 0 free, 1 pending, 2 launched; -1 bad argument                 */
+int32_t bd_batch_stats(bd_engine* e, int64_t* batches, int64_t* chunks);   /* CNN passes launched / chunks they carried */
+
+/* Pinned (page-locked) host memory for the streamer's chunk ring and for result buffers: what the new
+ * src/stream/worker.py:109-135 fills instead of fresh numpy arrays.  With pinned buffers bd_submit_* returns as soon
+ * as the copies are queued; with pageable input the host->device copy is staged synchronously by the driver, and
+ * pageable outputs are delivered through the slot's own pinned staging at bd_wait. */
+int32_t bd_host_alloc(size_t bytes, int32_t write_combined, void** out);
+void bd_host_free(void* p);
 
 /* Per-kernel-class device time of one un-graphed pass over device-resident audio (CUDA events around every
  * launch).  ms[BD_PROFILE_SLOTS] / launches[BD_PROFILE_SLOTS]: 0 frontend, 1 conv1, 2+i depthwise of layer i+2,

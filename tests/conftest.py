@@ -8,6 +8,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# the YAMNet blob is not in the reference checkout: tests run on the seeded synthetic network (explicit opt-in)
+os.environ.setdefault("BUZZ_B200_ALLOW_SYNTHETIC", "1")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 

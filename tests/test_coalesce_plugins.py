@@ -1,0 +1,229 @@
+"""GPU tests of the round-2 surfaces: chunk coalescing (several chunks in ONE pass of the CNN), the ticket API the
+plugins use, both embedder plugins' embed(), the embedder override hook (BASELINE config 5), the full 1-hour config
+against the ORACLE, the fp16 range guard, and detections at the reference's documented threshold (-1.2,
+models/model_general_v3/README.md:6)."""
+import os
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import yamnet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+THRESHOLD = -1.2          # /root/reference/models/model_general_v3/README.md:6
+
+
+# ------------------------------------------------------------------------------------------------ coalescing
+@pytest.mark.parametrize("hop", [96, 48])
+def test_coalesced_batches_are_bit_identical_to_single_chunks(engines, hop):
+    """Chunks launched together (one frontend launch over a segment table, one CNN pass) give the same bits as each
+    chunk on its own: every chunk is framed and padded independently (src/stream/worker.py:109-135)."""
+    e = engines("fp16x3", early_patches=64, late_patches=128, n_slots=16)
+    lens = [16000 * 10, 16000 * 3 + 77, 15600, 16000 * 20 + 1234, 400, 16000 * 7, 199 * 160 + 15360 * 3, 16000 * 12 + 5,
+            16000 * 9, 15360 * 4 + 240]
+    xs = [O.synth_audio(n, seed=40 + i) for i, n in enumerate(lens)]
+    want = [e.predict(x, hop) for x in xs]                      # one chunk per pass
+    b0, c0 = e.batch_stats
+    e.set_auto_flush(False)
+    try:
+        tks = [e.submit(x, hop) for x in xs]                    # all pending: nothing launched yet
+        e.flush()
+        got = [t.result() for t in tks]
+    finally:
+        e.set_auto_flush(True)
+    b1, c1 = e.batch_stats
+    assert c1 - c0 == len(xs)
+    assert b1 - b0 < len(xs), "chunks were not coalesced"
+    for g, w in zip(got, want):
+        assert g.shape == w.shape and np.array_equal(g, w)
+    # embeddings come out of a coalesced batch too
+    e.set_auto_flush(False)
+    try:
+        tks = [e.submit(x, hop, want_embeddings=True) for x in xs[:4]]
+        res = [t.result() for t in tks]
+    finally:
+        e.set_auto_flush(True)
+    for (a, emb), x in zip(res, xs):
+        a1, emb1 = e.predict(x, hop, want_embeddings=True)
+        assert np.array_equal(a, a1) and np.array_equal(emb, emb1)
+
+
+def test_coalesced_pcm_chunks_and_overflowing_batches(engines):
+    """int16 PCM chunks at two source rates, more patches than one late batch holds: the flush splits them into several
+    batches; results equal the one-at-a-time results."""
+    e = engines("fp16x3", early_patches=32, late_patches=64, n_slots=16)
+    rng = np.random.default_rng(3)
+    chunks = []
+    for i, (sr, ch, secs) in enumerate([(16000, 1, 30), (44100, 2, 21.5), (16000, 1, 40), (32000, 1, 12), (16000, 2, 33),
+                                        (48000, 1, 9.7)]):
+        n = int(sr * secs)
+        base = O.synth_audio(n, seed=60 + i)
+        pcm = np.clip(np.rint(base * 20000), -32768, 32767).astype(np.int16)
+        if ch == 2:
+            pcm = np.stack([pcm, np.roll(pcm, 7)], axis=1)
+        chunks.append((pcm, sr))
+    want = [e.predict_pcm(p, sr, 96) for p, sr in chunks]
+    e.set_auto_flush(False)
+    try:
+        tks = [e.submit_pcm(p, sr, 96) for p, sr in chunks]
+        got = [t.result() for t in tks]                         # the first wait launches everything pending
+    finally:
+        e.set_auto_flush(True)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+
+
+def test_auto_flush_under_load_and_two_threads(engines):
+    """The reference's thread layout: an inferer thread calls predict() per chunk, a writer thread calls
+    results.numpy() (src/inference/worker.py:71-92, src/write/worker.py:67-70).  Pinned input ring, pageable outputs."""
+    import queue
+    from buzzdetect_b200 import capi
+    e = engines("fp16x3", n_slots=16)
+    n = int(199.68 * 16000)
+    ring = [capi.pinned_empty(n, np.float32) for _ in range(6)]
+    src = [O.synth_audio(n, seed=80 + i) for i in range(6)]
+    for r, s in zip(ring, src):
+        r[:] = s
+    want = [e.predict(s, 96) for s in src]
+    q = queue.Queue()
+    got = {}
+
+    def writer():
+        while True:
+            item = q.get()
+            if item is None:
+                return
+            i, tk = item
+            got[i] = tk.result().copy()
+
+    th = threading.Thread(target=writer)
+    th.start()
+    order = [i % 6 for i in range(30)]
+    for k, i in enumerate(order):
+        q.put((k, e.submit(ring[i], 96)))
+    q.put(None)
+    th.join()
+    for k, i in enumerate(order):
+        assert np.array_equal(got[k], want[i]), k
+
+
+# ------------------------------------------------------------------------------------------------ plugins
+def test_both_embedder_plugins_embed_and_agree(engines, yamnet_variables, mel):
+    """load_embedder -> embed() for embedders/yamnet (Keras 3) and embedders/yamnet_k2; SURVEY 8d config 5: identical
+    outputs at hop 1 (the two graphs carry bit-identical mel constants and the same weights)."""
+    from buzzdetect_b200 import weights as W
+    from buzzdetect_b200.inference.embedding import load_embedder
+    x = O.synth_audio(16000 * 25 + 321, seed=12)
+    k3 = load_embedder("yamnet", framehop_prop=1, initialize=True)
+    k2 = load_embedder("yamnet_k2", framehop_prop=1, initialize=True)
+    assert k3.samplerate == k2.samplerate == 16000 and k3.n_embeddings == 1024
+    e3 = k3.embed(x).numpy()
+    e2 = k2.embed(x).numpy()
+    want = O.embed(x, yamnet_variables, mel, 96)
+    assert e3.shape == e2.shape == want.shape == (O.frame_counts(len(x), 96)[2], 1024)
+    assert float(np.abs(e2 - want).max() / np.abs(want).max()) <= 1e-4
+    assert np.array_equal(W.load_mel("yamnet"), W.load_mel("yamnet_k2"))
+    assert np.array_equal(e3, e2), "K3 and K2 embedders must agree bit for bit at hop 1"
+    # Keras-3 embedder at a hop the K2 plugin rejects but whole STFT frames allow (0.25 -> 24 frames)
+    k3q = load_embedder("yamnet", framehop_prop=0.25, initialize=True)
+    eq = k3q.embed(x).numpy()
+    assert eq.shape[0] == O.frame_counts(len(x), 24)[2]
+    wq = O.embed(x, yamnet_variables, mel, 24)
+    assert float(np.abs(eq - wq).max() / np.abs(wq).max()) <= 1e-4
+    with pytest.raises(ValueError):
+        load_embedder("yamnet_k2", framehop_prop=0.25, initialize=True)
+    k3.model.close(); k2.model.close(); k3q.model.close()
+
+
+def test_embedder_override_hook(monkeypatch, yamnet_variables, mel, head):
+    """model_general_v3 hard-codes embeddername='yamnet_k2' (reference model.py:8); BUZZ_B200_EMBEDDER swaps it."""
+    from buzzdetect_b200.inference.models import load_model
+    x = O.synth_audio(16000 * 14, seed=13)
+    m2 = load_model("model_general_v3", framehop_prop=1, initialize=True)
+    assert type(m2.embedder).__name__ == "YamnetK2"
+    a2 = m2.predict(x).numpy()
+    monkeypatch.setenv("BUZZ_B200_EMBEDDER", "yamnet")
+    m3 = load_model("model_general_v3", framehop_prop=1, initialize=True)
+    assert type(m3.embedder).__name__ == "EmbedderYamnet"
+    a3 = m3.predict(x).numpy()
+    assert np.array_equal(a2, a3)
+    want = O.predict(x, yamnet_variables, mel, head[0], head[1], 96)
+    assert float(np.abs(a3 - want).max()) <= 1e-3
+    m2.model.close(); m3.model.close()
+
+
+def test_plugin_predict_pcm_equals_resample_then_predict(engines):
+    from buzzdetect_b200.inference.models import load_model
+    m = load_model("model_general_v3", framehop_prop=1, initialize=True)
+    pcm = np.clip(np.rint(O.synth_audio(44100 * 9, seed=14) * 25000), -32768, 32767).astype(np.int16)
+    a = m.predict_pcm(pcm, 44100).numpy()
+    x16 = m.model.resample(pcm, 44100)
+    b = m.predict(x16).numpy()
+    assert np.array_equal(a, b)
+    m.model.close()
+
+
+# ------------------------------------------------------------------------------------------------ config 2 vs the oracle
+def test_one_hour_config_against_the_oracle(engines, yamnet_variables, mel, head):
+    """BASELINE configs[1] at full size (57.6 M samples, 3750 patches), default plan, against the float64-checked
+    oracle (not against another mode of the engine): max abs activation error <= 1e-3, zero detection flips at the
+    reference's threshold -1.2 outside a 1e-3 band."""
+    x = np.tile(O.synth_audio(300 * 16000, seed=91), 12)
+    assert x.size == 57_600_000
+    got, gemb = engines("fp16x3").predict(x, 96, want_embeddings=True)
+    want, wemb = O.predict(x, yamnet_variables, mel, head[0], head[1], 96, return_embeddings=True)
+    assert got.shape == want.shape == (3750, 13)
+    err = float(np.abs(got - want).max())
+    eerr = float(np.abs(gemb - wemb).max() / np.abs(wemb).max())
+    near = np.abs(want[:, 8] - THRESHOLD) <= 1e-3
+    flips = int(((got[:, 8] > THRESHOLD) != (want[:, 8] > THRESHOLD))[~near].sum())
+    from tests.test_gpu_parity import _report
+    _report("one_hour_vs_oracle", {"act_max_abs": err, "emb_max_rel": eerr, "flips_at_-1.2": flips,
+                                   "detections": int((want[:, 8] > THRESHOLD).sum()),
+                                   "rounded_cells_differing": int((np.round(got, 2) != np.round(want, 2)).sum())})
+    assert err <= 1e-3, err
+    assert eerr <= 1e-4, eerr
+    assert flips == 0
+
+
+# ------------------------------------------------------------------------------------------------ fp16 range guard
+def _scaled_variables(variables, layer, s):
+    """Multiply the depthwise OUTPUT of separable layer `layer` by s and divide it out again in the following pointwise
+    BN, so only that one tensor grows (BN has no gamma: scale = 1/sqrt(var + eps), embedders/yamnet/params.py:46-48)."""
+    eps = 1e-4
+    v = dict(variables)
+    b = 4 * (layer - 2) + 2
+    dw_bn, pw, pw_bn = f"layer_with_weights-{b + 1}", f"layer_with_weights-{b + 2}/kernel", f"layer_with_weights-{b + 3}"
+    var = v[dw_bn + "/moving_variance"].astype(np.float64)
+    v[dw_bn + "/moving_variance"] = ((var + eps) / s ** 2 - eps).astype(np.float32)
+    v[dw_bn + "/beta"] = (v[dw_bn + "/beta"].astype(np.float64) * s).astype(np.float32)
+    v[pw] = (v[pw].astype(np.float64) / s).astype(np.float32)
+    return v
+
+
+@pytest.mark.parametrize("layer", [2, 4, 7, 9, 13])
+def test_large_activations_do_not_overflow_fp16_operands(yamnet_variables, mel, head, layer):
+    """Depthwise outputs of ~1e5 (beyond fp16's 65504) feed the fp16 hi/lo split of every fused kernel family:
+    layer 2 (l12_fused2), 4 (sep_fused3), 7 (depthwise + pw_gemm), 9 (sep_fused3 whole-patch tiles), 13 (3x2 layers).
+    hi saturates, lo carries the rest: results stay finite and within tolerance of the oracle."""
+    from buzzdetect_b200 import capi
+    x = O.synth_audio(16000 * 6, seed=15)
+    taps = {}
+    O.embed(x, yamnet_variables, mel, 96, taps=taps)
+    peak = float(np.abs(taps[f"L{layer}dw"]).max())
+    s = 2.0 ** np.floor(np.log2(1.0e5 / peak))
+    v = _scaled_variables(yamnet_variables, layer, s)
+    taps2 = {}
+    want = O.predict(x, v, mel, head[0], head[1], 96)
+    O.embed(x, v, mel, 96, taps=taps2)
+    big = float(np.abs(taps2[f"L{layer}dw"]).max())
+    assert 65504 < big < 131008, big
+    e = capi.Engine(device=0, yamnet_variables=v, precision="fp16x3")
+    try:
+        got = e.predict(x, 96)
+    finally:
+        e.close()
+    assert np.isfinite(got).all()
+    assert float(np.abs(got - want).max()) <= 1e-3
