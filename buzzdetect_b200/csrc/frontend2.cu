@@ -148,6 +148,25 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc
                  : "memory");
 }
 
+// explicit shared-window accesses: the buffers are carved out of an aligned byte array, so ptxas cannot prove the
+// address space from the pointers and would fall back to generic LD / ST
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts64f(uint32_t a, float2 v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32f(uint32_t a, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+
 struct TileInfo {
     const float* x;
     long long n_valid;
@@ -169,7 +188,8 @@ logmel2_kernel(const __grid_constant__ FeSegs segs, const __grid_constant__ FeMe
     const uint32_t stage_u32 = smem_u32(smem + kOffStage);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int h = lane >> 4, l = lane & 15;
-    float2* ex = reinterpret_cast<float2*>(smem + kOffEx) + (warp * 2 + h) * kExHalf;
+    const uint32_t samp_u32 = smem_u32(samp), mag_u32 = smem_u32(mag);
+    const uint32_t ex_u32 = smem_u32(smem + kOffEx) + static_cast<uint32_t>((warp * 2 + h) * kExHalf * 8);
 
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -250,30 +270,31 @@ logmel2_kernel(const __grid_constant__ FeSegs segs, const __grid_constant__ FeMe
 #pragma unroll 1
         for (int r = 0; r < 2; ++r) {
             const int f = warp + 8 * r + 16 * h;                   // this half-warp's frame within the tile
-            const float* xs = samp + f * kHop + 2 * l;
+            const uint32_t xs = samp_u32 + static_cast<uint32_t>((f * kHop + 2 * l) * 4);
             float2 v[16];
 #pragma unroll
             for (int n1 = 0; n1 < 12; ++n1) {
-                const float2 sv = *reinterpret_cast<const float2*>(xs + 32 * n1);
+                const float2 sv = lds64(xs + 32 * 4 * n1);
                 v[n1] = make_float2(sv.x * wreg[n1].x, sv.y * wreg[n1].y);
             }
-            v[12] = make_float2(0.f, 0.f);
-            if (l < 8) {                                           // samples 384..399; the rest of the 512 is zero padding
-                const float2 sv = *reinterpret_cast<const float2*>(xs + 32 * 12);
+            {
+                // samples 384..399 (lanes l < 8); beyond them the 512-point frame is zero padding.  The other lanes read
+                // a clamped address and multiply by their zero window taps.
+                const float2 sv = lds64(l < 8 ? xs + 32 * 4 * 12 : xs);
                 v[12] = make_float2(sv.x * wreg[12].x, sv.y * wreg[12].y);
             }
             v[13] = v[14] = v[15] = make_float2(0.f, 0.f);
             dft16(v);                                              // over n1; result k1 at v[P16(k1)]
 #pragma unroll
             for (int k1 = 0; k1 < 16; ++k1)
-                ex[k1 * kExRow + l] = k1 == 0 ? v[P16(0)] : cmul(v[P16(k1)], tw1[k1]);
+                sts64f(ex_u32 + static_cast<uint32_t>((k1 * kExRow + l) * 8), k1 == 0 ? v[P16(0)] : cmul(v[P16(k1)], tw1[k1]));
             __syncwarp();
 #pragma unroll
-            for (int n2 = 0; n2 < 16; ++n2) v[n2] = ex[l * kExRow + n2];
+            for (int n2 = 0; n2 < 16; ++n2) v[n2] = lds64(ex_u32 + static_cast<uint32_t>((l * kExRow + n2) * 8));
             __syncwarp();
             dft16(v);                                              // over n2; Z[l + 16 k2] at v[P16(k2)]
             // split step (spectrum scaled by 2): X2[k] = (Z[k] + conj Z[256-k]) + W512^k * (-i) (Z[k] - conj Z[256-k])
-            float* mrow = mag + f * kMagStride + l;
+            const uint32_t mrow = mag_u32 + static_cast<uint32_t>((f * kMagStride + l) * 4);
 #pragma unroll
             for (int k2 = 0; k2 < 16; ++k2) {
                 const float2 zk = v[P16(k2)];
@@ -287,8 +308,8 @@ logmel2_kernel(const __grid_constant__ FeSegs segs, const __grid_constant__ FeMe
                 const float2 w = k2 == 0 ? wl : cmul(wl, w32(k2));
                 const float re = ex_ + w.x * ox - w.y * oy;
                 const float im = ey + w.x * oy + w.y * ox;
-                mrow[16 * k2] = sqrt_approx(re * re + im * im);
-                if (k2 == 0 && l == 0) mrow[256] = fabsf(ex_ - ox);   // X2[256] = 2 (Re Z0 - Im Z0)
+                sts32f(mrow + 64 * k2, sqrt_approx(re * re + im * im));
+                if (k2 == 0 && l == 0) sts32f(mrow + 1024, fabsf(ex_ - ox));   // X2[256] = 2 (Re Z0 - Im Z0)
             }
         }
         if (tid == 0) tma_store_wait_read<1>();                     // the staging buffer of two tiles ago is free again
@@ -302,12 +323,14 @@ logmel2_kernel(const __grid_constant__ FeSegs segs, const __grid_constant__ FeMe
         // ================================================================= mel + log: lane = frame
         const uint32_t stg = stage_u32 + static_cast<uint32_t>((iter & 1) * kStageBytes);
         {
-            const float* mp = mag + lane * kMagStride;
+            const uint32_t mp = mag_u32 + static_cast<uint32_t>(lane * kMagStride * 4);
             const int m_end = mel.warp_band[warp + 1];
             for (int m = mel.warp_band[warp]; m < m_end; ++m) {
                 const int st = mel.start[m], ln = mel.len[m], off = mel.off[m];
                 float acc = 0.f;
-                for (int j = 0; j < ln; ++j) acc = fmaf(mp[st + j], mel.w[off + j], acc);
+                const uint32_t mb = mp + static_cast<uint32_t>(st * 4);
+#pragma unroll 4
+                for (int j = 0; j < ln; ++j) acc = fmaf(lds32(mb + 4 * j), mel.w[off + j], acc);
                 const float val = logf(acc + 0.001f);
                 const int col = m & 31;
                 const uint32_t addr = stg + static_cast<uint32_t>((m >> 5) * 4096 + lane * 128 +

@@ -112,7 +112,7 @@ def test_auto_flush_under_load_and_two_threads(engines):
 # ------------------------------------------------------------------------------------------------ plugins
 def test_both_embedder_plugins_embed_and_agree(engines, yamnet_variables, mel):
     """load_embedder -> embed() for embedders/yamnet (Keras 3) and embedders/yamnet_k2; SURVEY 8d config 5: identical
-    outputs at hop 1 (the two graphs carry bit-identical mel constants and the same weights)."""
+    outputs at hop 1 (same weights; the graphs' mel constants differ in the 6th digit, see below)."""
     from buzzdetect_b200 import weights as W
     from buzzdetect_b200.inference.embedding import load_embedder
     x = O.synth_audio(16000 * 25 + 321, seed=12)
@@ -124,8 +124,15 @@ def test_both_embedder_plugins_embed_and_agree(engines, yamnet_variables, mel):
     want = O.embed(x, yamnet_variables, mel, 96)
     assert e3.shape == e2.shape == want.shape == (O.frame_counts(len(x), 96)[2], 1024)
     assert float(np.abs(e2 - want).max() / np.abs(want).max()) <= 1e-4
-    assert np.array_equal(W.load_mel("yamnet"), W.load_mel("yamnet_k2"))
-    assert np.array_equal(e3, e2), "K3 and K2 embedders must agree bit for bit at hop 1"
+    # The reference's two graphs do NOT carry the same mel constant: embedders/yamnet/saved_model.pb and
+    # embedders/yamnet_k2/.../saved_model.pb differ in 20 of the 461 non-zero weights by <= 6.2e-6
+    # (tools/extract_assets.py), so "identical" can only mean identical up to that: embeddings within 1e-5 of each
+    # other, and both within tolerance of the oracle run with their own constant.
+    m3, m2 = W.load_mel("yamnet"), W.load_mel("yamnet_k2")
+    assert int((m3 != m2).sum()) == 20 and float(np.abs(m3 - m2).max()) < 7e-6
+    assert float(np.abs(e3 - e2).max() / np.abs(e2).max()) <= 1e-5
+    want3 = O.embed(x, yamnet_variables, m3, 96)
+    assert float(np.abs(e3 - want3).max() / np.abs(want3).max()) <= 1e-4
     # Keras-3 embedder at a hop the K2 plugin rejects but whole STFT frames allow (0.25 -> 24 frames)
     k3q = load_embedder("yamnet", framehop_prop=0.25, initialize=True)
     eq = k3q.embed(x).numpy()
@@ -148,7 +155,8 @@ def test_embedder_override_hook(monkeypatch, yamnet_variables, mel, head):
     m3 = load_model("model_general_v3", framehop_prop=1, initialize=True)
     assert type(m3.embedder).__name__ == "EmbedderYamnet"
     a3 = m3.predict(x).numpy()
-    assert np.array_equal(a2, a3)
+    assert float(np.abs(a2 - a3).max()) <= 1e-4          # the two embedders' mel constants differ by <= 6.2e-6
+    assert np.array_equal(a2 > THRESHOLD, a3 > THRESHOLD)
     want = O.predict(x, yamnet_variables, mel, head[0], head[1], 96)
     assert float(np.abs(a3 - want).max()) <= 1e-3
     m2.model.close(); m3.model.close()
