@@ -6,15 +6,22 @@
         bench.py --gpus N --steps K --warmup W
 
 One "step" = one pass of the hot path (frontend -> YAMNet MobileNet-v1 -> model_general_v3 head) over one synthetic
-1-hour 16 kHz mono recording per GPU (BASELINE.json configs[1]; 57.6 M float32 samples = 230 MB, larger than the
-126 MB L2, so every step re-reads its audio from HBM).  Files shard across GPUs with no collective (weak scaling).
+1-hour 16 kHz mono recording per GPU (BASELINE.json configs[1]; 57.6 M samples, larger than the 126 MB L2, so every
+step re-reads its audio from HBM).  Files shard across GPUs with no collective (weak scaling).
 
-  value : audio-hours / s with the audio already resident in HBM, timed with CUDA events on the engine's stream
-  e2e   : the same metric through the reference-facing C ABI with HOST (pinned) buffers: per-chunk H2D of the
-          samples and D2H of the activations inside the timed region, chunks pipelined over bd_submit_host/bd_wait
-  roofline     : pointwise (1x1) GEMMs, the dominant kernel class -- algorithmic TFLOP/s against the measured bf16 peak
+  value      : audio-hours / s with the audio already resident in HBM, CUDA events on the engine's stream
+  e2e        : the same metric through the reference-facing PLUGIN: load_model('model_general_v3') and one predict call
+               per 199.68 s chunk (the reference's default chunking) from ONE inferer thread, results.numpy() on a
+               writer thread (src/inference/worker.py:71-92, src/write/worker.py:67-70).  Chunks lie in pinned host
+               memory as int16 PCM -- the file pipeline's feed -- and every chunk's host->device copy and every
+               result's device->host copy are inside the timed region.  (= e2e_pcm16)
+  e2e_plugin : the same with float32 samples through predict() (the reference streamer's dtype; PCIe-bound)
+  e2e_plugin_pageable / e2e_slots : pageable numpy input; the raw bd_submit_host / bd_wait C-ABI leg
+  configs    : BASELINE configs[4] (half hop) and configs[2] (44.1 kHz stereo int16 streamed in chunks) on the same path
+  roofline / rooflines : per kernel family against MEASURED_PEAKS.json (algorithmic bytes or flops / CUDA-event time)
   cpu_baseline : the oracle (numpy/torch-CPU restatement of the reference's TensorFlow path) on this box's cores
-  --impl reference : only the CPU oracle is timed (TensorFlow/librosa are not installable here)
+  --impl reference : the CPU oracle on all host cores over the same workload (TensorFlow/librosa cannot be installed
+               here and the YAMNet blob is missing from the checkout)
 """
 from __future__ import annotations
 
@@ -43,6 +50,7 @@ HOP_FRAMES = 96
 PW_FLOP_PER_PATCH = 132_120_576
 DW_BYTES_PER_PATCH = 2_445_312
 FRONTEND_BYTES_PER_PATCH = 86_016
+FE_WARP_INSTR_PER_FRAME = 450          # logmel2_kernel: 707 SASS instructions per two-frame FFT round + the mel phase
 TOTAL_FLOP_PER_PATCH = 137_289_728
 METRIC = "audio-hours processed/sec (realtime factor) at 1/2/4/8 B200 vs host-CPU ref"
 UNIT = "audio-hours/s"
@@ -113,8 +121,10 @@ def dist_setup(n_gpus: int):
 
 
 # ----------------------------------------------------------------------------------------------- CPU oracle timing
-def time_oracle(steps: int, warmup: int, chunk_s: float = 199.68, chunks_per_step: int = 1):
-    """The restated reference path on the host cores: reference chunking (199.68 s), all threads."""
+def time_oracle(steps: int, warmup: int, hours_per_step: float = 1.0, chunk_s: float = 199.68, seed: int = 1000,
+                budget_s: float = 200.0):
+    """The restated reference path on the host cores: one synthetic recording of `hours_per_step` per step, cut into
+    the reference's default 199.68 s chunks (src/analyze.py:102-111), every chunk through predict(), all threads."""
     import numpy as np
     import torch
     from buzzdetect_b200 import weights as W
@@ -124,38 +134,65 @@ def time_oracle(steps: int, warmup: int, chunk_s: float = 199.68, chunks_per_ste
     variables, prov = W.resolve_yamnet(verify=False)
     hk, hb = W.load_head()
     mel = W.load_mel()
-    n = int(round(chunk_s * SR))
-    xs = [O.synth_audio(n, seed=100 + i) for i in range(chunks_per_step)]
+    n = int(round(hours_per_step * HOUR_SAMPLES))
+    base = O.synth_audio(60 * SR, seed=seed)
+    x = np.tile(base, -(-n // base.size))[:n]
+    chunk_n = int(round(chunk_s * SR))
+    chunks = [x[o:o + chunk_n] for o in range(0, n, chunk_n)]
+
+    # bounded: one chunk is timed first; if the whole run would exceed the budget on this host, a step covers only the
+    # first k chunks of the recording (said in `sample`; rates are per audio actually processed)
+    t0 = time.perf_counter()
+    O.predict(chunks[0], variables, mel, hk, hb, HOP_FRAMES)
+    t_chunk = time.perf_counter() - t0
+    k = len(chunks)
+    if (steps + warmup) * k * t_chunk > budget_s:
+        k = max(1, int(budget_s / ((steps + warmup) * t_chunk)))
+    used = chunks[:k]
+    audio_h = sum(c.size for c in used) / HOUR_SAMPLES
+
+    def one_step():
+        for c in used:
+            O.predict(c, variables, mel, hk, hb, HOP_FRAMES)
+
     for _ in range(warmup):
-        O.predict(xs[0], variables, mel, hk, hb, HOP_FRAMES)
+        one_step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        for x in xs:
-            O.predict(x, variables, mel, hk, hb, HOP_FRAMES)
+        one_step()
     dt = time.perf_counter() - t0
-    hours = steps * chunks_per_step * chunk_s / 3600.0
-    return hours / dt, dt, cores, f"{steps}x{chunks_per_step} chunk(s) of {chunk_s} s (reference default chunking), " \
-                                  f"oracle = torch-CPU/numpy restatement, weights {prov.split(':')[0]}"
+    hours = steps * audio_h
+    what = (f"the whole {hours_per_step:g}-hour recording ({len(chunks)} chunks of {chunk_s} s)" if k == len(chunks) else
+            f"the first {k} of {len(chunks)} chunks of {chunk_s} s of the {hours_per_step:g}-hour recording (time budget)")
+    return hours / dt, dt, cores, (f"{steps} step(s) over {what}, reference default chunking, {warmup} warm-up step(s); "
+                                  f"oracle = torch-CPU/numpy restatement on {cores} threads, weights {prov.split(':')[0]}")
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    steps, warmup = max(args.steps, 1), max(args.warmup, 1)
-    value, dt, cores, sample = time_oracle(steps, min(warmup, 2))
+    from buzzdetect_b200 import probe
+    steps, warmup = max(args.steps, 1), max(args.warmup, 0)
+    value, dt, cores, sample = time_oracle(steps, warmup, args.hours)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(warmup, 2), "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "synthetic 16 kHz mono, YAMNet + model_general_v3, hop 1 (configs[1] sampled: "
-                               "one 199.68 s chunk per step)", "chunk_s": 199.68},
+        "config": workload_config(args.hours),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "reference_runtime": probe.reference_runtime(),
         "note": "TensorFlow/librosa are absent from this image and the YAMNet blob is absent from the reference "
-                "checkout, so the reference arm is the CPU oracle port (DESIGN.md)",
+                "checkout, so the reference arm is the CPU oracle port on all host cores (DESIGN.md section 8)",
     }
     print(json.dumps(line), flush=True)
+
+
+def workload_config(hours):
+    return {"workload": f"synthetic {hours:g}-hour 16 kHz mono recording per GPU, YAMNet + model_general_v3, hop "
+                        f"{HOP_FRAMES / 96:g} (BASELINE configs[{1 if HOP_FRAMES == 96 else 4}])",
+            "chunk_s": 199.68}
 
 
 def bind_to_gpu_numa_node(dev: int):
@@ -185,6 +222,94 @@ def bind_to_gpu_numa_node(dev: int):
         return f"numa: bound to node {node} ({len(allowed)} cpus)"
     except Exception as exc:                                          # noqa: BLE001 -- diagnostics only
         return f"numa: not bound ({type(exc).__name__})"
+
+
+# ----------------------------------------------------------------------------------------------- configs 3 and 5
+def run_extra_configs(args, rank, world, dev, eng, model, d_x, d_act, n, hv, use_dist, dist, capi, np, torch):
+    """BASELINE configs[4] (yamnet_k2 at hop 0.5) and configs[2] (44.1 kHz stereo int16 streamed in 199.68 s chunks)
+    through the same plugin path, one recording-hour each; reported beside the headline, never instead of it."""
+    import queue
+    from buzzdetect_b200.inference.models import load_model
+    from oracle import yamnet_oracle as O
+    out = {}
+    hours = n / HOUR_SAMPLES
+
+    def through_plugin(m, feed_chunks, rate, steps):
+        def run(k):
+            q = queue.Queue(maxsize=args.slots)
+
+            def writer():
+                while True:
+                    item = q.get()
+                    if item is None:
+                        return
+                    item.numpy()
+
+            th = threading.Thread(target=writer)
+            th.start()
+            for _ in range(k):
+                for c in feed_chunks:
+                    q.put(m.predict_pcm(c, rate))
+            q.put(None)
+            th.join()
+
+        run(2)
+        m.model.synchronize()
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run(steps)
+        m.model.synchronize()
+        torch.cuda.synchronize()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if use_dist:
+            dist.barrier()
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return world * hours * steps / float(tt.item())
+
+    steps = max(1, min(args.steps, 3))
+    # ---- config 5 / configs[4]: half hop (7499 patches per audio-hour): device-resident and through the plugin
+    _, _, P48 = capi.frames_for(n, 48)
+    d_act48 = torch.empty((P48, eng.n_classes), dtype=torch.float32, device="cuda")
+    for _ in range(2):
+        eng.predict_device_ptr(d_x.data_ptr(), n, 48, d_act48.data_ptr())
+    ms48 = eng.bench_device_ptr(d_x.data_ptr(), n, 48, d_act48.data_ptr(), steps)
+    t48 = torch.tensor([ms48], dtype=torch.float64, device="cuda")
+    if use_dist:
+        dist.all_reduce(t48, op=dist.ReduceOp.MAX)
+    m48 = load_model("model_general_v3", framehop_prop=0.5, initialize=True)
+    chunk_n = int(round(args.chunk_s * SR))
+    pcm16 = capi.pinned_empty(n, np.int16)
+    pcm16[:] = np.clip(np.rint(hv * 32768.0), -32768, 32767).astype(np.int16)
+    feed = [pcm16[o:o + chunk_n] for o in range(0, n, chunk_n)]
+    out["hop48"] = {"value": world * hours * steps / (float(t48.item()) / 1e3), "e2e": through_plugin(m48, feed, SR, steps),
+                    "unit": UNIT, "patches_per_step_per_gpu": P48,
+                    "what": "BASELINE configs[4]: yamnet_k2 halfhop (framehop_prop 0.5) + model_general_v3; e2e = plugin "
+                            "predict_pcm per 199.68 s chunk, pinned int16"}
+    m48.model.close()
+    del d_act48, feed, pcm16
+    # ---- config 3 / configs[2]: 44.1 kHz stereo int16 streamed in the reference's 199.68 s chunks (one hour of the
+    # day-long recording per step): raw PCM over PCIe, downmix + resample + path on the device
+    sr3 = 44100
+    n3 = int(round(hours * 3600 * sr3))
+    base = O.synth_audio(60 * sr3, seed=2000 + rank, sr=sr3)
+    b16 = np.clip(np.rint(base * 32768.0), -32768, 32767).astype(np.int16)
+    pcm3 = capi.pinned_empty((n3, 2), np.int16)
+    for off in range(0, n3, b16.size):
+        k = min(b16.size, n3 - off)
+        pcm3[off:off + k, 0] = b16[:k]
+        pcm3[off:off + k, 1] = np.roll(b16, 37)[:k]
+    chunk3 = int(args.chunk_s * sr3)                       # int(chunk[1] * sr): src/stream/worker.py:110-112
+    feed3 = [pcm3[o:o + chunk3] for o in range(0, n3, chunk3)]
+    out["cfg3_44k1_stereo_int16"] = {
+        "e2e": through_plugin(model, feed3, sr3, steps), "unit": UNIT, "h2d_bytes_per_step": int(pcm3.nbytes),
+        "chunks_per_step": len(feed3),
+        "what": "BASELINE configs[2], one hour of the recording per step: 44.1 kHz stereo int16 in pinned host memory, "
+                "199.68 s chunks through predict_pcm (downmix + tcgen05 resampler + path on the device); the resume run "
+                "is a parity test (tests/test_writer_pipeline.py), not a timing"}
+    del feed3, pcm3
+    return out
 
 
 # ----------------------------------------------------------------------------------------------- our arm
@@ -257,67 +382,129 @@ def run_ours(args, rank, world, local):
     ms_max = float(t.item())
     value = world * hours_per_step * args.steps / (ms_max / 1000.0)
 
-    # ---------------- end to end through the C ABI with host buffers
+    # ---------------- end to end through the reference-facing plugin (load_model -> predict per chunk)
+    # Thread layout of the reference: ONE inferer thread calls model.predict(chunk) per 199.68 s chunk
+    # (src/inference/worker.py:71-92) and hands the result to the writer thread, which calls results.numpy()
+    # (src/write/worker.py:67-70).  The chunks lie in PINNED host memory, as the pinned-buffer streamer leaves them.
+    # Host->device copy of every chunk and device->host copy of every result are inside the timed region.
+    import queue
+    os.environ["BUZZ_B200_DEVICE"] = str(dev)
+    os.environ["BUZZ_B200_PRECISION"] = args.precision
+    os.environ["BUZZ_B200_SLOTS"] = str(args.slots)
+    from buzzdetect_b200.inference.models import load_model
+    framehop_prop = HOP_FRAMES / 96.0
+    model = load_model("model_general_v3", framehop_prop=framehop_prop, initialize=True)
+    pcm16 = capi.pinned_empty(n, np.int16)
+    pcm16[:] = np.clip(np.rint(hv * 32768.0), -32768, 32767).astype(np.int16)
     chunk_n = int(round(args.chunk_s * SR))
-    chunks = [(o, min(chunk_n, n - o)) for o in range(0, n, chunk_n)]
-    outs = []
-    for (o, m) in chunks:
-        _, _, p = capi.frames_for(m, HOP_FRAMES)
-        outs.append(torch.empty((p, eng.n_classes), dtype=torch.float32).pin_memory())
-    n_slots = 4
+    bounds = [(o, min(chunk_n, n - o)) for o in range(0, n, chunk_n)]
 
-    def e2e_run(steps, pcm16=None):
-        """`steps` recordings back to back; chunks stay pipelined across recordings (a streamer never drains the
-        GPU between files), everything is drained before the clock stops.  pcm16: the same recording as int16 PCM,
-        submitted through the PCM entry point (what a WAV streamer holds: half the bytes over PCIe)."""
+    def plugin_run(steps, feed):
+        """`steps` recordings back to back through the plugin; returns patches written by the writer thread."""
+        q = queue.Queue(maxsize=args.slots)
+        done = {"rows": 0}
+
+        def writer():
+            while True:
+                item = q.get()
+                if item is None:
+                    return
+                done["rows"] += item.numpy().shape[0]
+
+        th = threading.Thread(target=writer)
+        th.start()
+        for _ in range(steps):
+            for (o, m) in bounds:
+                if feed == "f32":
+                    q.put(model.predict(hv[o:o + m]))
+                elif feed == "pcm16":
+                    q.put(model.predict_pcm(pcm16[o:o + m], SR))
+                else:
+                    q.put(model.predict(pageable[o:o + m]))
+        q.put(None)
+        th.join()
+        return done["rows"]
+
+    def timed_plugin(feed, steps):
+        plugin_run(max(args.warmup, 3), feed)
+        model.model.synchronize()
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        b0, c0 = model.model.batch_stats
+        t0 = time.perf_counter()
+        rows = plugin_run(steps, feed)
+        model.model.synchronize()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        b1, c1 = model.model.batch_stats
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if use_dist:
+            dist.barrier()
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        assert rows == steps * sum(capi.frames_for(m, HOP_FRAMES)[2] for _, m in bounds)
+        return {"value": world * hours_per_step * steps / float(tt.item()), "unit": UNIT,
+                "chunks_per_pass": round((c1 - c0) / max(b1 - b0, 1), 2), "passes": int(b1 - b0)}
+
+    d2h_bytes = sum(capi.frames_for(m, HOP_FRAMES)[2] for _, m in bounds) * eng.n_classes * 4
+    e2e_pcm16 = timed_plugin("pcm16", args.steps)
+    e2e_pcm16.update({"h2d_bytes_per_step": n * 2, "d2h_bytes_per_step": d2h_bytes, "chunk_s": args.chunk_s,
+                      "chunks_per_step": len(bounds), "entry": "load_model('model_general_v3').predict_pcm(int16 chunk, 16000) "
+                      "per chunk from one inferer thread, results.numpy() on a writer thread; pinned int16 PCM (what a WAV "
+                      "streamer holds), converted on the device"})
+    e2e_plugin = timed_plugin("f32", args.steps)
+    e2e_plugin.update({"h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": d2h_bytes, "chunk_s": args.chunk_s,
+                       "chunks_per_step": len(bounds), "entry": "load_model('model_general_v3').predict(float32 chunk) per chunk, "
+                       "pinned float32 samples (the reference streamer's dtype): 230 MB per audio-hour over PCIe"})
+    pageable = np.array(hv, copy=True)
+    e2e_pageable = timed_plugin("pageable", max(1, args.steps // 2))
+    e2e_pageable.update({"h2d_bytes_per_step": n * 4, "entry": "the same with pageable numpy input (host->device copies are "
+                         "staged synchronously by the driver)"})
+    del pageable
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- the raw C-ABI slot leg (bd_submit_host / bd_wait, no plugin objects), longer chunks
+    slot_chunk_n = int(round(args.slot_chunk_s * SR))
+    chunks = [(o, min(slot_chunk_n, n - o)) for o in range(0, n, slot_chunk_n)]
+    outs = [torch.empty((capi.frames_for(m, HOP_FRAMES)[2], eng.n_classes), dtype=torch.float32).pin_memory()
+            for (_, m) in chunks]
+    n_slots = 16
+    slot_eng = capi.Engine(device=dev, precision=args.precision, early_patches=args.early, late_patches=args.late,
+                           n_slots=n_slots, fuse_mask=args.fuse_mask)
+
+    def slots_run(steps):
         j = 0
         for _ in range(steps):
             for i, (o, m) in enumerate(chunks):
-                s = j % n_slots
+                sl = j % n_slots
                 j += 1
-                eng.wait(s)
-                if pcm16 is None:
-                    eng.submit_ptr(s, host.data_ptr() + 4 * o, m, HOP_FRAMES, outs[i].data_ptr())
-                else:
-                    eng.submit_pcm_ptr(s, pcm16.data_ptr() + 2 * o, 1, 1, m, SR, HOP_FRAMES, outs[i].data_ptr())
-        for s in range(n_slots):
-            eng.wait(s)
+                slot_eng.wait(sl)
+                slot_eng.submit_ptr(sl, host.data_ptr() + 4 * o, m, HOP_FRAMES, outs[i].data_ptr())
+        for sl in range(n_slots):
+            slot_eng.wait(sl)
 
-    e2e_run(max(args.warmup, 3))
-    eng.synchronize()
+    slots_run(max(args.warmup, 3))
+    slot_eng.synchronize()
     if use_dist:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    e2e_run(args.steps)
-    eng.synchronize()
+    slots_run(args.steps)
+    slot_eng.synchronize()
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if use_dist:
         dist.barrier()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * hours_per_step * args.steps / float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
-    d2h_bytes = sum(o.numel() * 4 for o in outs)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_slots = {"value": world * hours_per_step * args.steps / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": n * 4,
+                 "chunk_s": args.slot_chunk_s, "slots": n_slots, "entry": "bd_submit_host / bd_wait, pinned float32"}
+    slot_eng.close()
 
-    # the same end-to-end leg fed with int16 PCM (bd_submit_pcm_host): reported beside `e2e`, never instead of it
-    pcm16 = torch.from_numpy(np.clip(np.rint(hv * 32768.0), -32768, 32767).astype(np.int16)).pin_memory()
-    e2e_run(2, pcm16)
-    eng.synchronize()
-    if use_dist:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    e2e_run(args.steps, pcm16)
-    eng.synchronize()
-    torch.cuda.synchronize()
-    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    if use_dist:
-        dist.barrier()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_pcm16_value = world * hours_per_step * args.steps / float(t.item())
-    del pcm16
+    # ---------------- BASELINE configs 3 and 5 through the same plugin path
+    extra_configs = {}
+    if not args.no_configs:
+        extra_configs = run_extra_configs(args, rank, world, dev, eng, model, d_x, d_act, n, hv, use_dist,
+                                          dist if use_dist else None, capi, np, torch)
 
     # ---------------- the stage in front of the path for non-16 kHz input (BASELINE configs[2]): downmix + resample of
     # one audio-hour of 44.1 kHz stereo int16 PCM already in HBM (synchronous C-ABI call, wall clock around it)
@@ -386,12 +573,12 @@ def run_ours(args, rank, world, local):
                             "bytes": FRONTEND_BYTES_PER_PATCH * float(P)}
     total_prof_ms = sum(prof[k]["ms"] for k in ("frontend", "conv1", "depthwise", "pointwise", "pool_head"))
     traffic_tab = {}
-    tpath = os.path.join(ROOT, "profiles", "traffic_r1e.json")
-    if not os.path.exists(tpath):
-        tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
+    import glob
+    tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_*.json")), key=os.path.getmtime)
+    if tfiles:
+        with open(tfiles[-1]) as f:
             traffic_tab = json.load(f)
+        traffic_tab["_file"] = os.path.basename(tfiles[-1])
     rooflines = {}
     for nm, f in fam.items():
         if f["ms"] <= 0:
@@ -405,7 +592,8 @@ def run_ours(args, rank, world, local):
                          "algorithmic_per_launch": (f["flop"] if tens else f["bytes"]) / max(f["launches"], 1),
                          "avg_launch_ms": f["ms"] / max(f["launches"], 1),
                          "traffic": traffic_tab.get(nm, {}).get("dram_bytes_per_launch")}
-        rooflines[nm]["traffic_source"] = traffic_tab.get("_source") if rooflines[nm]["traffic"] else None
+        rooflines[nm]["traffic_source"] = (f"{traffic_tab.get('_file')}: {traffic_tab.get('_source')}"
+                                           if rooflines[nm]["traffic"] else None)
         if tens:
             rooflines[nm]["executed_mma_factor"] = mma_factor
             rooflines[nm]["hbm_gbs"] = f["bytes"] / (f["ms"] / 1e3) / 1e9
@@ -419,27 +607,42 @@ def run_ours(args, rank, world, local):
         else "algorithmic bytes (fp32 in + out)"
     stages = {k: prof[k] for k in ("frontend", "conv1", "depthwise", "pointwise", "pool_head")}
 
+    # the frontend sits at the FP32-issue side of the ridge: report that bound beside HBM
+    fe = rooflines.get("logmel_kernel")
+    if fe is not None:
+        frames = (P - 1) * HOP_FRAMES + 96
+        warp_instr = frames * FE_WARP_INSTR_PER_FRAME
+        sm_clock_hz = (clocks or {}).get("sm_mhz") or 1965.0
+        ideal_ms = warp_instr / (148 * 4 * sm_clock_hz * 1e6) * 1e3
+        fe["issue_bound"] = {"warp_instructions_per_frame": FE_WARP_INSTR_PER_FRAME, "ideal_ms_at_4_ipc_per_sm": ideal_ms,
+                             "frac": ideal_ms / fe["ms"], "note": "512-point fp32 FFT + split + mel: SASS instruction count "
+                             "of logmel2_kernel per frame against one instruction per scheduler per clock"}
+
     if rank == 0:
-        cpu_v, cpu_dt, cores, sample = time_oracle(steps=2, warmup=1) if (world == 1 and not args.no_cpu) else (None,) * 4
+        from buzzdetect_b200 import probe
+        cpu_v, cpu_dt, cores, sample = time_oracle(steps=2, warmup=1, hours_per_step=hours_per_step, budget_s=30.0) \
+            if (world == 1 and not args.no_cpu) else (None,) * 4
+        cfgd = workload_config(hours_per_step)
+        cfgd.update({"patches_per_step_per_gpu": P, "pointwise_precision": args.precision,
+                     "weights": eng.weights_provenance.split(":")[0],
+                     "l2": "input (230 MB/step) larger than L2; no explicit flush",
+                     "early_patches": args.early, "late_patches": args.late, "fuse_mask": args.fuse_mask,
+                     "plugin_slots": args.slots, "sharding": "one file per GPU, no collective", "host": numa_note})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision != "fp16" else "f16",
             "data": "synthetic",
-            "config": {"workload": f"synthetic {hours_per_step:g}-hour 16 kHz mono recording per GPU, YAMNet + "
-                                   f"model_general_v3, hop {HOP_FRAMES / 96:g} (BASELINE configs[{1 if HOP_FRAMES == 96 else 4}])",
-                       "patches_per_step_per_gpu": P, "pointwise_precision": args.precision,
-                       "weights": eng.weights_provenance.split(":")[0],
-                       "l2": "input (230 MB/step) larger than L2; no explicit flush", "e2e_chunk_s": args.chunk_s,
-                       "early_patches": args.early, "late_patches": args.late, "fuse_mask": args.fuse_mask,
-                       "sharding": "one file per GPU, no collective", "host": numa_note},
+            "config": cfgd,
             "realtime_factor": value * 3600.0,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": d2h_bytes,
-                    "chunks_per_step": len(chunks), "slots": n_slots,
-                    "note": "float32 samples from pinned host memory (230 MB per audio-hour: PCIe-bound above ~240 "
-                            "audio-hours/s per GPU)"},
-            "e2e_pcm16": {"value": e2e_pcm16_value, "unit": UNIT, "h2d_bytes_per_step": n * 2,
-                          "d2h_bytes_per_step": d2h_bytes, "entry": "bd_submit_pcm_host (int16 PCM, converted on the device)"},
+            # headline: the plugin path fed the way the file pipeline feeds it (pinned int16 PCM chunks of 199.68 s)
+            "e2e": dict(e2e_pcm16),
+            "e2e_pcm16": e2e_pcm16,
+            "e2e_plugin": e2e_plugin,
+            "e2e_plugin_pageable": e2e_pageable,
+            "e2e_slots": e2e_slots,
+            "e2e_over_value": {"pcm16": e2e_pcm16["value"] / value, "plugin_f32": e2e_plugin["value"] / value},
+            "configs": extra_configs,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
@@ -448,6 +651,7 @@ def run_ours(args, rank, world, local):
             "resample_stage": resample_stage,
             "layers": per_layer,
             "whole_path_tflops": TOTAL_FLOP_PER_PATCH * P * world * args.steps / (ms_max / 1000.0) / 1e12,
+            "reference_runtime": probe.reference_runtime(),
         }
         if cpu_v is not None:
             line["cpu_baseline"] = {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
@@ -455,6 +659,7 @@ def run_ours(args, rank, world, local):
     if use_dist:
         dist.barrier()
         dist.destroy_process_group()
+    model.model.close()
     eng.close()
 
 
@@ -468,8 +673,12 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("BUZZ_B200_PRECISION", "fp16x3"),
                     choices=["fp16x3", "fp16", "fp32"])
     ap.add_argument("--hours", type=float, default=1.0, help="audio hours per step per GPU")
-    ap.add_argument("--chunk-s", dest="chunk_s", type=float, default=599.04,
-                    help="chunk length of the end-to-end (host buffer) leg; multiple of 0.96 s")
+    ap.add_argument("--chunk-s", dest="chunk_s", type=float, default=199.68,
+                    help="chunk length of the plugin end-to-end legs (reference default: 199.68 s)")
+    ap.add_argument("--slot-chunk-s", dest="slot_chunk_s", type=float, default=599.04,
+                    help="chunk length of the raw bd_submit_host leg")
+    ap.add_argument("--slots", type=int, default=48, help="chunks in flight through the plugin (engine slots)")
+    ap.add_argument("--no-configs", dest="no_configs", action="store_true", help="skip the configs 3 / 5 legs")
     ap.add_argument("--early", type=int, default=0)
     ap.add_argument("--late", type=int, default=0)
     ap.add_argument("--fuse-mask", dest="fuse_mask", type=int, default=-1,

@@ -309,9 +309,10 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 }
 
 // ------------------------------------------------------------------------------------------ fp16 operand range guard
-// Post-ReLU activations become fp16 hi (+ lo) planes for the tensor cores.  hi saturates at fp16's largest finite value
-// and lo carries what is left, so an activation up to 131,008 keeps its ~22 significant bits and nothing ever turns
-// into inf (a real checkpoint's activations are O(1)..O(100); the guard costs one FMNMX per conversion).
+// Post-ReLU activations become fp16 hi (+ lo) planes for the tensor cores.  They arrive here pre-scaled by 2^-4 (the
+// engine folds that factor into the depthwise taps, engine.cu:bd_engine_create), so anything up to ~1e6 keeps its ~22
+// significant bits; beyond that hi saturates at fp16's largest finite value (and lo carries what it can) instead of
+// turning into inf.  A real checkpoint's activations are O(1)..O(100); the guard costs one FMNMX per conversion.
 __device__ __forceinline__ __half half_sat(float x) { return __float2half_rn(fminf(x, 65504.f)); }
 
 // ------------------------------------------------------------------------------------------ misc

@@ -42,9 +42,9 @@ struct LogmelSeg {                 // one independent chunk of 16 kHz audio insi
     int row_begin;                 // first row of the shared log-mel buffer this segment writes
     int n_rows;                    // number of frames
 };
-struct FrontendMelParam { unsigned char raw[2880]; };   // opaque image of the kernel's mel parameter block
+struct alignas(16) FrontendMelParam { unsigned char raw[4912]; };   // opaque image of the kernel's mel parameter block
 cudaError_t frontend2_init_device();
-void frontend2_build_mel(const FrontendTables& tab, FrontendMelParam* out);
+bool frontend2_build_mel(const FrontendTables& tab, FrontendMelParam* out);   // false: mel matrix too dense
 cudaError_t launch_logmel_segs(const LogmelSeg* segs, int n_segs, const FrontendMelParam& mel, const float* window,
                                float* logmel, long long logmel_rows, int num_sms, cudaStream_t stream);
 

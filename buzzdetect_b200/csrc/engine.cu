@@ -143,6 +143,7 @@ struct bd_engine {
 namespace {
 
 thread_local std::string g_create_error;
+constexpr float kActScale = 0.0625f;      // power of two applied to the depthwise outputs in the tensor-core modes
 
 #define BD_CHECK(e, expr)                                                                       \
     do {                                                                                        \
@@ -712,8 +713,20 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
 
     // ---- weights
     e->h_folded.assign(w->folded, w->folded + w->folded_len);
+    if (e->precision != BD_PRECISION_FP32_SIMT) {
+        // fp16 operand headroom: the depthwise taps and biases are scaled by 2^-4 (exact), so every depthwise output
+        // reaches the fp16 hi/lo split 16 times smaller and the pointwise epilogue multiplies it back (out_scale).
+        // Activations up to ~1e6 then keep their full 22 bits (beyond that half_sat() saturates instead of producing
+        // inf); post-ReLU values below ~1e-3 fall into fp16's subnormal range, an absolute error < 1e-6.
+        for (int L = 1; L < BD_N_LAYERS; ++L) {
+            const bd_layer_desc& d = w->layers[L];
+            if (d.dw_w < 0 || d.dw_b < 0) continue;
+            for (int i = 0; i < 9 * d.cin; ++i) e->h_folded[d.dw_w + i] *= kActScale;
+            for (int i = 0; i < d.cin; ++i) e->h_folded[d.dw_b + i] *= kActScale;
+        }
+    }
     BD_CREATE(cudaMalloc(&e->d_folded, w->folded_len * sizeof(float)));
-    BD_CREATE(cudaMemcpy(e->d_folded, w->folded, w->folded_len * sizeof(float), cudaMemcpyHostToDevice));
+    BD_CREATE(cudaMemcpy(e->d_folded, e->h_folded.data(), w->folded_len * sizeof(float), cudaMemcpyHostToDevice));
     BD_CREATE(cudaMalloc(&e->d_headW, sizeof(float) * kEmb * w->n_classes));
     BD_CREATE(cudaMemcpy(e->d_headW, w->head_kernel, sizeof(float) * kEmb * w->n_classes, cudaMemcpyHostToDevice));
     BD_CREATE(cudaMalloc(&e->d_headB, sizeof(float) * w->n_classes));
@@ -736,7 +749,7 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
             for (int j = 0; j < len; ++j) t.mel_w[off + j] = w->mel[(first + j) * kMel + m];
             off += len;
         }
-        frontend2_build_mel(t, &e->mel_param);
+        if (!frontend2_build_mel(t, &e->mel_param)) return bail("mel matrix does not fit the frontend's band tables");
         BD_CREATE(cudaMalloc(&e->d_tab, sizeof(FrontendTables)));
         BD_CREATE(cudaMemcpy(e->d_tab, &t, sizeof(t), cudaMemcpyHostToDevice));
     }
@@ -810,7 +823,7 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
             LayerDev& l = e->layers[L];
             const size_t nw = static_cast<size_t>(l.d.cout) * l.d.cin;
             std::vector<__half> hi(nw), lo(nw);
-            const float out_scale = split_weights_f16(w->folded + l.d.w, nw, hi.data(), lo.data());
+            const float out_scale = split_weights_f16(w->folded + l.d.w, nw, hi.data(), lo.data()) / kActScale;
             BD_CREATE(cudaMalloc(&l.w_hi, nw * sizeof(__half)));
             BD_CREATE(cudaMalloc(&l.w_lo, nw * sizeof(__half)));
             BD_CREATE(cudaMemcpy(l.w_hi, hi.data(), nw * sizeof(__half), cudaMemcpyHostToDevice));
@@ -1374,8 +1387,8 @@ int32_t bd_debug_stage(bd_engine* e, const float* samples, int64_t n, int32_t ho
             if (e->precision == BD_PRECISION_FP16X3)
                 cudaMemcpy(lo.data(), static_cast<const unsigned char*>(src) + plane_off, count * sizeof(__half),
                            cudaMemcpyDeviceToHost);
-            for (int64_t i = 0; i < count; ++i)
-                out[i] = __half2float(hi[i]) + (e->precision == BD_PRECISION_FP16X3 ? __half2float(lo[i]) : 0.f);
+            for (int64_t i = 0; i < count; ++i)      // undo the 2^-4 operand scale (see bd_engine_create)
+                out[i] = (__half2float(hi[i]) + (e->precision == BD_PRECISION_FP16X3 ? __half2float(lo[i]) : 0.f)) / kActScale;
         }
         if (rc == 0 && n_out) *n_out = count;
     }

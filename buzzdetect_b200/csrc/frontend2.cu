@@ -24,6 +24,8 @@
 //
 // A launch covers a table of segments (independent chunks of audio, each framed and padded on its own, exactly as the
 // reference treats chunks): segment s writes log-mel rows [row_begin, row_begin + n_rows) of one shared buffer.
+#include <cstring>
+
 #include "bd_common.cuh"
 #include "bd_kernels.cuh"
 
@@ -35,7 +37,8 @@ constexpr int kTileFrames = 32;
 constexpr int kFeWarps = 8;
 constexpr int kFeThreads = kFeWarps * 32;
 constexpr int kTileSamples = (kTileFrames - 1) * kHop + kWin;   // 5360 floats = 21,440 B
-constexpr int kMagStride = 257;                                 // odd: lane = frame reads hit 32 different banks
+constexpr int kMagStride = 260;                                 // 16-byte rows: the mel phase reads four bins per LDS.128
+constexpr int kMelGroupsMax = 256;                              // 4-bin groups over all bands (shipped matrix: ~170)
 constexpr int kExRow = 17;                                      // float2 per transpose row (16 + 1 pad)
 constexpr int kExHalf = 16 * kExRow;                            // one frame's 16 x 16 transpose buffer
 constexpr int kStageBytes = 2 * 4096;                           // [32 frames x 64 bands] as two swizzled 32-column blocks
@@ -50,11 +53,12 @@ static_assert(kOffSamples % 16 == 0 && kOffEx % 8 == 0 && kOffBar % 8 == 0, "fro
 static_assert(2 * (kFe2Smem + 1024) <= 228 * 1024, "two CTAs per SM");
 
 struct FeMel {                     // kernel parameter (constant bank): uniform reads cost no L1/shared traffic
-    int start[kMel];
-    int len[kMel];
-    int off[kMel];
-    int warp_band[kFeWarps + 1];   // warp w computes bands [warp_band[w], warp_band[w+1]) (balanced by non-zeros)
-    float w[kMelNnzMax];           // 0.5 * mel weight: the split step leaves the spectrum scaled by 2 (exact)
+    float4 w4[kMelGroupsMax];      // 0.5 * mel weights in groups of four consecutive bins (zero outside the band); the
+                                   // factor 0.5 undoes the split step's scale of 2 (exact)
+    int gbin[kMel];                // first bin of the band's first group (a multiple of 4)
+    int glen[kMel];                // number of groups
+    int goff[kMel];                // index of the band's first group in w4
+    int warp_band[kFeWarps + 1];   // warp w computes bands [warp_band[w], warp_band[w+1]) (balanced by work)
 };
 
 struct FeSeg {
@@ -142,6 +146,14 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     return y;
 }
 
+// log(x) = log2(x) * ln 2 with the hardware approximation: absolute error <= 2^-21.4 for x in [0.5, 2], 3 ulp elsewhere
+// (CUDA C++ Programming Guide, intrinsic table) -- below 2e-6 over the log-mel range, against ~30 instructions for logf
+__device__ __forceinline__ float log_fast(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y * 0.69314718055994531f;
+}
+
 __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
                  "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
@@ -218,6 +230,8 @@ logmel2_kernel(const __grid_constant__ FeSegs segs, const __grid_constant__ FeMe
         wl = make_float2(cs, sn);
     }
     const int src_lane = ((16 - l) & 15) + 16 * h;            // holder of Z[256 - k] for this lane's bins
+    // the padding bins 257..259 of every magnitude row meet zero weights in the mel phase: keep them finite
+    for (int i = tid; i < kTileFrames * 3; i += kFeThreads) mag[(i / 3) * kMagStride + 257 + i % 3] = 0.f;
 
     auto tile_info = [&](int t) {
         TileInfo ti;
@@ -269,7 +283,9 @@ logmel2_kernel(const __grid_constant__ FeSegs segs, const __grid_constant__ FeMe
         // ================================================================= FFT: warp = frames (fi, fi + 16), two rounds
 #pragma unroll 1
         for (int r = 0; r < 2; ++r) {
-            const int f = warp + 8 * r + 16 * h;                   // this half-warp's frame within the tile
+            // this half-warp's frame within the tile; the two halves are 4 frames apart so that their magnitude rows
+            // (260 floats each) fall into disjoint bank halves
+            const int f = (warp & 3) + 4 * h + 8 * (warp >> 2) + 16 * r;
             const uint32_t xs = samp_u32 + static_cast<uint32_t>((f * kHop + 2 * l) * 4);
             float2 v[16];
 #pragma unroll
@@ -293,23 +309,31 @@ logmel2_kernel(const __grid_constant__ FeSegs segs, const __grid_constant__ FeMe
             for (int n2 = 0; n2 < 16; ++n2) v[n2] = lds64(ex_u32 + static_cast<uint32_t>((l * kExRow + n2) * 8));
             __syncwarp();
             dft16(v);                                              // over n2; Z[l + 16 k2] at v[P16(k2)]
-            // split step (spectrum scaled by 2): X2[k] = (Z[k] + conj Z[256-k]) + W512^k * (-i) (Z[k] - conj Z[256-k])
+            // split step (spectrum scaled by 2): with xe2 = Z[k] + conj Z[256-k], xo2 = -i (Z[k] - conj Z[256-k]) and
+            // t = W512^k xo2:   X2[k] = xe2 + t   and   X2[256-k] = conj(xe2 - t).
+            // A lane takes its own bins with k2 = 0..7 and produces BOTH magnitudes of each pair; the partner lane
+            // (16 - l) does the same from its side, which covers this lane's bins with k2 = 8..15.
             const uint32_t mrow = mag_u32 + static_cast<uint32_t>((f * kMagStride + l) * 4);
+            const uint32_t mrow_c = mag_u32 + static_cast<uint32_t>((f * kMagStride + 256 - l) * 4);
 #pragma unroll
-            for (int k2 = 0; k2 < 16; ++k2) {
+            for (int k2 = 0; k2 < 8; ++k2) {
                 const float2 zk = v[P16(k2)];
                 const float2 pub = v[P16(15 - k2)];                // what the partner lane needs from this lane
                 float2 zc;
                 zc.x = __shfl_sync(0xFFFFFFFFu, pub.x, src_lane);
                 zc.y = __shfl_sync(0xFFFFFFFFu, pub.y, src_lane);
-                if (l == 0) zc = v[P16((16 - k2) & 15)];           // bins 16 k2 mirror inside lane 0
+                if (l == 0) zc = v[P16((16 - k2) & 15)];           // bins 16 k2 mirror inside lane 0 (bin 0 pairs with 256)
                 const float ex_ = zk.x + zc.x, ey = zk.y - zc.y;
                 const float ox = zk.y + zc.y, oy = zc.x - zk.x;
                 const float2 w = k2 == 0 ? wl : cmul(wl, w32(k2));
-                const float re = ex_ + w.x * ox - w.y * oy;
-                const float im = ey + w.x * oy + w.y * ox;
+                const float tx = w.x * ox - w.y * oy, ty = w.x * oy + w.y * ox;
+                const float re = ex_ + tx, im = ey + ty, rc = ex_ - tx, ic = ey - ty;
                 sts32f(mrow + 64 * k2, sqrt_approx(re * re + im * im));
-                if (k2 == 0 && l == 0) sts32f(mrow + 1024, fabsf(ex_ - ox));   // X2[256] = 2 (Re Z0 - Im Z0)
+                sts32f(mrow_c - 64 * k2, sqrt_approx(rc * rc + ic * ic));
+            }
+            if (l == 0) {                                           // bin 128 pairs with itself: |X2[128]| = 2 |Z[128]|
+                const float2 z = v[P16(8)];
+                sts32f(mrow + 64 * 8, 2.f * sqrt_approx(z.x * z.x + z.y * z.y));
             }
         }
         if (tid == 0) tma_store_wait_read<1>();                     // the staging buffer of two tiles ago is free again
@@ -326,12 +350,18 @@ logmel2_kernel(const __grid_constant__ FeSegs segs, const __grid_constant__ FeMe
             const uint32_t mp = mag_u32 + static_cast<uint32_t>(lane * kMagStride * 4);
             const int m_end = mel.warp_band[warp + 1];
             for (int m = mel.warp_band[warp]; m < m_end; ++m) {
-                const int st = mel.start[m], ln = mel.len[m], off = mel.off[m];
+                const int gl = mel.glen[m], go = mel.goff[m];
+                const uint32_t mb = mp + static_cast<uint32_t>(mel.gbin[m] * 4);
                 float acc = 0.f;
-                const uint32_t mb = mp + static_cast<uint32_t>(st * 4);
-#pragma unroll 4
-                for (int j = 0; j < ln; ++j) acc = fmaf(lds32(mb + 4 * j), mel.w[off + j], acc);
-                const float val = logf(acc + 0.001f);
+                for (int g = 0; g < gl; ++g) {
+                    const float4 x = lds128(mb + 16 * g);
+                    const float4 w = mel.w4[go + g];
+                    acc = fmaf(x.x, w.x, acc);
+                    acc = fmaf(x.y, w.y, acc);
+                    acc = fmaf(x.z, w.z, acc);
+                    acc = fmaf(x.w, w.w, acc);
+                }
+                const float val = log_fast(acc + 0.001f);
                 const int col = m & 31;
                 const uint32_t addr = stg + static_cast<uint32_t>((m >> 5) * 4096 + lane * 128 +
                                                                  ((((col >> 2) ^ (lane & 7))) << 4) + (col & 3) * 4);
@@ -369,26 +399,38 @@ cudaError_t frontend2_init_device() {
     return cudaFuncSetAttribute(logmel2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFe2Smem);
 }
 
-void frontend2_build_mel(const FrontendTables& tab, FrontendMelParam* out_raw) {
+bool frontend2_build_mel(const FrontendTables& tab, FrontendMelParam* out_raw) {
     static_assert(sizeof(FrontendMelParam) >= sizeof(FeMel), "FrontendMelParam too small");
     FeMel& m = *reinterpret_cast<FeMel*>(out_raw);
-    int total = 0;
+    std::memset(&m, 0, sizeof(m));
+    int groups = 0, total = 0;
+    int cost[kMel];
     for (int b = 0; b < kMel; ++b) {
-        m.start[b] = tab.mel_start[b];
-        m.len[b] = tab.mel_len[b];
-        m.off[b] = tab.mel_off[b];
-        total += tab.mel_len[b] + 24;                              // + the band's log / store cost in tap units
+        const int st = tab.mel_start[b], ln = tab.mel_len[b];
+        const int g0 = (st / 4) * 4;
+        const int gl = ln > 0 ? (st + ln - g0 + 3) / 4 : 0;
+        if (groups + gl > kMelGroupsMax || g0 + 4 * gl > kMagStride) return false;
+        m.gbin[b] = g0;
+        m.glen[b] = gl;
+        m.goff[b] = groups;
+        for (int j = 0; j < ln; ++j) {
+            const int k = st + j - g0;
+            reinterpret_cast<float*>(&m.w4[groups + k / 4])[k % 4] = 0.5f * tab.mel_w[tab.mel_off[b] + j];
+        }
+        groups += gl;
+        cost[b] = 6 * gl + 16;                                     // instructions per band: groups + log / store
+        total += cost[b];
     }
-    for (int i = 0; i < kMelNnzMax; ++i) m.w[i] = 0.5f * tab.mel_w[i];
     // contiguous band ranges per warp, balanced by work
     int b = 0, acc = 0;
     m.warp_band[0] = 0;
     for (int w = 1; w < kFeWarps; ++w) {
         const int target = static_cast<int>(static_cast<long long>(total) * w / kFeWarps);
-        while (b < kMel && acc + (tab.mel_len[b] + 24) / 2 < target) { acc += tab.mel_len[b] + 24; ++b; }
+        while (b < kMel && acc + cost[b] / 2 < target) { acc += cost[b]; ++b; }
         m.warp_band[w] = b;
     }
     m.warp_band[kFeWarps] = kMel;
+    return true;
 }
 
 cudaError_t launch_logmel_segs(const LogmelSeg* segs, int n_segs, const FrontendMelParam& mel_raw, const float* window,

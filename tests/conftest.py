@@ -59,3 +59,28 @@ def engines(built_lib, yamnet_variables):
     yield get
     for e in cache.values():
         e.close()
+
+
+_REPORT = {}
+
+
+def report(key, val):
+    """Append a measured number to gpurun_out/parity_report.json (read back into profiles/ and DESIGN.md)."""
+    import json
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        path = os.path.join(out, "parity_report.json")
+        if not _REPORT and os.path.exists(path):
+            with open(path) as f:
+                _REPORT.update(json.load(f))          # several pytest invocations append to one report
+        _REPORT[key] = val
+        with open(path, "w") as f:
+            json.dump(_REPORT, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+@pytest.fixture(scope="session")
+def parity_report():
+    return report

@@ -10,10 +10,9 @@ from oracle import yamnet_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def test_true_parity_when_the_reference_runtime_is_present(engines, mel):
-    from tests.test_gpu_parity import _report
+def test_true_parity_when_the_reference_runtime_is_present(engines, mel, parity_report):
     rt = probe.reference_runtime()
-    _report("reference_runtime", rt)
+    parity_report("reference_runtime", rt)
     if not rt["complete"]:
         pytest.skip(f"reference runtime absent on this box: {rt}")
     e = engines("fp32")
@@ -23,12 +22,12 @@ def test_true_parity_when_the_reference_runtime_is_present(engines, mel):
     want = probe.tf_log_mel(xp, mel)
     got = e.debug_logmel(x, nf)
     err = float(np.abs(got - want[:nf]).max())
-    _report("true_parity_logmel_vs_tensorflow", err)
+    parity_report("true_parity_logmel_vs_tensorflow", err)
     assert err <= 1e-4
     src = O.synth_audio(44100 * 5, seed=22, sr=44100)
     want = probe.librosa_resample(src, 44100)
     got = e.resample(src, 44100)
     assert got.shape == want.shape
     delta = float(np.abs(got - want).max())
-    _report("true_parity_resample_vs_soxr", delta)
+    parity_report("true_parity_resample_vs_soxr", delta)
     assert delta <= 1e-3
