@@ -413,6 +413,7 @@ def run_ours(args, rank, world, local):
 
         th = threading.Thread(target=writer)
         th.start()
+        t_sub = time.perf_counter()
         for _ in range(steps):
             for (o, m) in bounds:
                 if feed == "f32":
@@ -421,6 +422,7 @@ def run_ours(args, rank, world, local):
                     q.put(model.predict_pcm(pcm16[o:o + m], SR))
                 else:
                     q.put(model.predict(pageable[o:o + m]))
+        plugin_run.submit_s = time.perf_counter() - t_sub
         q.put(None)
         th.join()
         return done["rows"]
@@ -444,7 +446,8 @@ def run_ours(args, rank, world, local):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         assert rows == steps * sum(capi.frames_for(m, HOP_FRAMES)[2] for _, m in bounds)
         return {"value": world * hours_per_step * steps / float(tt.item()), "unit": UNIT,
-                "chunks_per_pass": round((c1 - c0) / max(b1 - b0, 1), 2), "passes": int(b1 - b0)}
+                "chunks_per_pass": round((c1 - c0) / max(b1 - b0, 1), 2), "passes": int(b1 - b0),
+                "wall_s": dt, "inferer_loop_s": plugin_run.submit_s}
 
     d2h_bytes = sum(capi.frames_for(m, HOP_FRAMES)[2] for _, m in bounds) * eng.n_classes * 4
     e2e_pcm16 = timed_plugin("pcm16", args.steps)

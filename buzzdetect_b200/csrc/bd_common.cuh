@@ -174,6 +174,17 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, ui
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f8f6f4 (8-bit float inputs, fp32 accumulate), K = 32 per instruction.
+__device__ __forceinline__ void umma_f8_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -225,6 +236,28 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
            | (0u << 16)         // b_major = K
            | ((N >> 3) << 17)   // n_dim
            | ((M >> 4) << 24);  // m_dim
+}
+
+// cute::UMMA::InstrDescriptor for kind::f8f6f4 with both operands E5M2 (format 1), fp32 accumulate, both K-major.
+__host__ __device__ constexpr uint32_t umma_idesc_e5m2(uint32_t M, uint32_t N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------ fp16 + fp8 operand plan
+// "fp16f8": C = A_hi W_hi (fp16) + [A_lo 2^11 | A_hi] . [W_hi 2^-11 | W_lo] (e5m2), i.e. the two correction products of
+// the hi/lo split run as ONE fp8 contraction of twice the length -- 2 MMA-equivalents per k-step instead of 3, half the
+// operand bytes for the corrections.  A correction term is ~2^-11 of the main product, so e5m2's 2-bit mantissa leaves
+// a relative error of ~2^-14 (simulated end to end: tools/precision_ladder.py, 5e-5 max abs on the logits).
+// e5m2 has fp16's exponent range, so anything representable in the fp16 planes converts without overflow.
+constexpr float kF8LoScale = 2048.f;            // A_lo is stored times 2^11, W_hi times 2^-11
+__device__ __forceinline__ uint32_t pack_e5m2x4(float a, float b, float c, float d) {
+    uint16_t lo, hi;
+    asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));   // first source -> upper byte
+    asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+    return static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+}
+__device__ __forceinline__ void sts32u(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------ CTA pairs (cta_group::2)

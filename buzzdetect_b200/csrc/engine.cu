@@ -15,7 +15,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -62,6 +64,10 @@ struct Slot {
     int64_t n = 0, P = 0;
     int hop = 0;
     bool want_emb = false;
+    // decoded-PCM chunks: downmix + resample run on the compute stream at the head of the pass that takes the chunk
+    bool has_pcm = false;
+    int pcm_fmt = 0, pcm_channels = 1, pcm_rate = 16000;
+    int64_t pcm_frames = 0;
     cudaEvent_t ev_in = nullptr, ev_comp = nullptr, ev_out = nullptr;
     int state = 0;                  // 0 free, 1 pending (input on its way, compute not enqueued), 2 launched
 };
@@ -112,8 +118,14 @@ struct bd_engine {
     float* d_emb_batch[2] = {nullptr, nullptr};
     cudaEvent_t ev_batch_out[2] = {nullptr, nullptr};
     int batch_set = 0;
-    cudaEvent_t ev_last_comp = nullptr;   // end of the most recently enqueued compute (GPU-idle test for auto-flush)
-    bool any_launched = false;
+    // dispatcher: one thread per engine launches what is pending as soon as the GPU has room (at most two passes in the
+    // stream) and the first pending chunk has arrived -- work-conserving dynamic batching, independent of how the
+    // caller's threads are scheduled (a Python writer thread may sit behind the GIL for milliseconds)
+    std::thread dispatcher;
+    std::condition_variable_any cv_work, cv_launched;
+    bool stop = false, flush_req = false;
+    cudaEvent_t ev_pass[2] = {nullptr, nullptr};   // end of compute of pass i (i & 1)
+    int64_t pass_seq = 0;
     int64_t batches = 0, batched_chunks = 0;
     bool auto_flush = true;               // bd_set_auto_flush(0): chunks wait until bd_wait / bd_flush (tests, batch drivers)
     int64_t coalesce_target = 3072;       // pending patches that trigger a launch even while the GPU is busy
@@ -139,6 +151,12 @@ struct bd_engine {
     std::map<int, Resampler> resamplers;
     std::string last_error;
 };
+
+extern "C" {
+static int get_resampler(bd_engine* e, int src_rate, bd_engine::Resampler** out);
+static int run_resample(bd_engine* e, const bd_engine::Resampler* r, const void* d_in, int fmt, int channels,
+                        long long n_frames, float* d_out, long long no, cudaStream_t st);
+}
 
 namespace {
 
@@ -473,12 +491,23 @@ struct SlotOut { float* act; float* emb; };
 // all of them (a 208-patch chunk on its own leaves most of the 148 persistent CTAs of every kernel idle).
 int launch_group(bd_engine* e, const std::vector<int>& group, const std::vector<SlotOut>& outs) {
     const int hop = e->slots[group[0]].hop;
-    for (int si : group) BD_CHECK(e, cudaStreamWaitEvent(e->s_compute, e->slots[si].ev_in, 0));
+    cudaEvent_t ev_pass = e->ev_pass[e->pass_seq & 1];
+    e->pass_seq++;
+    for (int si : group) {
+        Slot& s = e->slots[si];
+        BD_CHECK(e, cudaStreamWaitEvent(e->s_compute, s.ev_in, 0));
+        if (s.has_pcm) {
+            bd_engine::Resampler ident{1, 1, 1, nullptr};
+            bd_engine::Resampler* r = &ident;
+            if (s.pcm_rate != 16000 && get_resampler(e, s.pcm_rate, &r)) return 1;
+            if (run_resample(e, r, s.d_pcm, s.pcm_fmt, s.pcm_channels, s.pcm_frames, s.d_in, s.n, e->s_compute)) return 1;
+        }
+    }
     if (group.size() == 1) {
         Slot& s = e->slots[group[0]];
         if (run_chunk(e, s.d_in, s.n, hop, s.d_act, s.want_emb ? s.d_emb : nullptr, s.P, s.P >= 512)) return 1;
         BD_CHECK(e, cudaEventRecord(s.ev_comp, e->s_compute));
-        BD_CHECK(e, cudaEventRecord(e->ev_last_comp, e->s_compute));
+        BD_CHECK(e, cudaEventRecord(ev_pass, e->s_compute));
         BD_CHECK(e, cudaStreamWaitEvent(e->s_out, s.ev_comp, 0));
         BD_CHECK(e, cudaMemcpyAsync(outs[0].act, s.d_act, s.P * e->n_classes * sizeof(float), cudaMemcpyDeviceToHost, e->s_out));
         if (s.want_emb)
@@ -517,7 +546,7 @@ int launch_group(bd_engine* e, const std::vector<int>& group, const std::vector<
         return 1;
     Slot& s0 = e->slots[group[0]];
     BD_CHECK(e, cudaEventRecord(s0.ev_comp, e->s_compute));
-    BD_CHECK(e, cudaEventRecord(e->ev_last_comp, e->s_compute));
+    BD_CHECK(e, cudaEventRecord(ev_pass, e->s_compute));
     BD_CHECK(e, cudaStreamWaitEvent(e->s_out, s0.ev_comp, 0));
     for (size_t i = 0; i < group.size(); ++i) {
         Slot& s = e->slots[group[i]];
@@ -533,9 +562,10 @@ int launch_group(bd_engine* e, const std::vector<int>& group, const std::vector<
     return 0;
 }
 
-// Launch everything that is pending, grouped into batches of chunks with the same hop that fit one late batch.
+// Launch pending chunks, grouped into passes of chunks with the same hop that fit one late batch.  only_arrived: stop at
+// the first chunk whose input is still on its way and launch ONE pass (dispatcher); otherwise everything (explicit flush).
 // Caller holds e->mu.  On failure the affected slots are released (state 0) so the engine stays usable.
-int flush_pending(bd_engine* e) {
+int launch_pending(bd_engine* e, bool only_arrived) {
     size_t pos = 0;
     int rc = 0;
     while (pos < e->pending.size() && rc == 0) {
@@ -548,6 +578,7 @@ int flush_pending(bd_engine* e) {
             Slot& s = e->slots[e->pending[pos]];
             if (s.hop != hop) break;
             if (!group.empty() && g + tail_slots + s.P > e->S2) break;
+            if (only_arrived && !group.empty() && cudaEventQuery(s.ev_in) != cudaSuccess) { cudaGetLastError(); break; }
             g += (group.empty() ? 0 : tail_slots) + s.P;
             group.push_back(e->pending[pos]);
             outs.push_back(SlotOut{s.dst_act, s.want_emb ? s.dst_emb : nullptr});
@@ -556,30 +587,56 @@ int flush_pending(bd_engine* e) {
         }
         rc = launch_group(e, group, outs);
         for (int si : group) e->slots[si].state = rc == 0 ? 2 : 0;
+        if (only_arrived) break;
     }
     if (rc != 0)
         for (; pos < e->pending.size(); ++pos) e->slots[e->pending[pos]].state = 0;
-    else
-        e->any_launched = true;
-    e->pending.clear();
+    e->pending.erase(e->pending.begin(), e->pending.begin() + static_cast<long>(std::min(pos, e->pending.size())));
+    if (rc != 0) e->pending.clear();
+    e->cv_launched.notify_all();
     return rc;
 }
 
-bool gpu_idle(bd_engine* e) {
-    if (!e->any_launched) return true;
-    const cudaError_t q = cudaEventQuery(e->ev_last_comp);
-    if (q == cudaErrorNotReady) { cudaGetLastError(); return false; }
-    return true;
+int flush_pending(bd_engine* e) { return launch_pending(e, false); }
+
+void dispatcher_main(bd_engine* e) {
+    cudaSetDevice(e->device);
+    std::unique_lock<std::recursive_mutex> lk(e->mu);
+    while (true) {
+        e->cv_work.wait(lk, [&] { return e->stop || (!e->pending.empty() && (e->auto_flush || e->flush_req)); });
+        if (e->stop) return;
+        if (e->flush_req) {                         // explicit flush: everything, whatever has or has not arrived
+            e->flush_req = false;
+            launch_pending(e, false);
+            continue;
+        }
+        // at most two passes in the stream: the one running and the one queued behind it
+        cudaEvent_t gate = e->ev_pass[e->pass_seq & 1];
+        if (e->pass_seq >= 2 && cudaEventQuery(gate) == cudaErrorNotReady) {
+            cudaGetLastError();
+            lk.unlock();
+            cudaEventSynchronize(gate);
+            lk.lock();
+            continue;                               // re-evaluate: more chunks may have been queued meanwhile
+        }
+        cudaGetLastError();
+        // the first pending chunk must have reached the device (a pass that waits for PCIe blocks the ones behind it)
+        cudaEvent_t first = e->slots[e->pending[0]].ev_in;
+        if (cudaEventQuery(first) == cudaErrorNotReady) {
+            cudaGetLastError();
+            lk.unlock();
+            cudaEventSynchronize(first);
+            lk.lock();
+            continue;
+        }
+        cudaGetLastError();
+        launch_pending(e, true);
+    }
 }
 
-// After a chunk has been queued: launch now when the GPU has nothing to do (latency) or when a full batch is waiting;
-// otherwise let chunks accumulate behind the running batch (throughput: they will run as ONE pass).
+// A chunk has been queued: wake the dispatcher.
 int maybe_flush(bd_engine* e) {
-    int64_t patches = 0;
-    for (int si : e->pending) patches += e->slots[si].P;
-    if (!e->auto_flush) return 0;
-    if (patches >= e->coalesce_target || static_cast<int>(e->pending.size()) >= kMaxLogmelSegs || gpu_idle(e))
-        return flush_pending(e);
+    e->cv_work.notify_one();
     return 0;
 }
 
@@ -628,6 +685,14 @@ int64_t bd_launch_count(const bd_engine* e) { return e ? e->launch_count : 0; }
 
 void bd_engine_destroy(bd_engine* e) {
     if (!e) return;
+    if (e->dispatcher.joinable()) {
+        {
+            std::lock_guard<std::recursive_mutex> lk(e->mu);
+            e->stop = true;
+        }
+        e->cv_work.notify_all();
+        e->dispatcher.join();
+    }
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
@@ -635,7 +700,7 @@ void bd_engine_destroy(bd_engine* e) {
         cudaFree(e->d_act_batch[i]); cudaFree(e->d_emb_batch[i]);
         if (e->ev_batch_out[i]) cudaEventDestroy(e->ev_batch_out[i]);
     }
-    if (e->ev_last_comp) cudaEventDestroy(e->ev_last_comp);
+    for (int i = 0; i < 2; ++i) if (e->ev_pass[i]) cudaEventDestroy(e->ev_pass[i]);
     for (auto& s : e->slots) {
         cudaFree(s.d_in); cudaFree(s.d_pcm); cudaFree(s.d_act); cudaFree(s.d_emb);
         if (s.h_act) cudaFreeHost(s.h_act);
@@ -851,7 +916,7 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
     int ns = cfg->n_slots <= 0 ? 2 : std::min(cfg->n_slots, 64);
     e->slots.resize(ns);
     for (int i = 0; i < 2; ++i) BD_CREATE(cudaEventCreateWithFlags(&e->ev_batch_out[i], cudaEventDisableTiming));
-    BD_CREATE(cudaEventCreateWithFlags(&e->ev_last_comp, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) BD_CREATE(cudaEventCreateWithFlags(&e->ev_pass[i], cudaEventDisableTiming));
     e->coalesce_target = std::max<int64_t>(1, static_cast<int64_t>(e->S2) * 3 / 4);
     if (const char* ct = getenv("BD_COALESCE_PATCHES")) e->coalesce_target = std::max<int64_t>(1, atoll(ct));
     for (auto& s : e->slots) {
@@ -861,24 +926,33 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
     }
     BD_CREATE(cudaDeviceSynchronize());
 #undef BD_CREATE
+    e->dispatcher = std::thread(dispatcher_main, e);
     *out = e;
+    return 0;
+}
+
+// explicit flush: hand everything pending to the dispatcher and wait until it has been launched
+static int flush_and_wait_launched(bd_engine* e, std::unique_lock<std::recursive_mutex>& lk) {
+    if (e->pending.empty()) return 0;
+    e->flush_req = true;
+    e->cv_work.notify_one();
+    e->cv_launched.wait(lk, [&] { return e->pending.empty() || e->stop; });
     return 0;
 }
 
 int32_t bd_flush(bd_engine* e) {
     if (!e) return 1;
-    std::lock_guard<std::recursive_mutex> lk(e->mu);
-    BD_CHECK(e, cudaSetDevice(e->device));
-    return flush_pending(e);
+    std::unique_lock<std::recursive_mutex> lk(e->mu);
+    return flush_and_wait_launched(e, lk);
 }
 
 int32_t bd_synchronize(bd_engine* e) {
     if (!e) return 1;
     {
-        std::lock_guard<std::recursive_mutex> lk(e->mu);
-        BD_CHECK(e, cudaSetDevice(e->device));
-        if (flush_pending(e)) return 1;
+        std::unique_lock<std::recursive_mutex> lk(e->mu);
+        flush_and_wait_launched(e, lk);
     }
+    BD_CHECK(e, cudaSetDevice(e->device));
     BD_CHECK(e, cudaStreamSynchronize(e->s_in));
     BD_CHECK(e, cudaStreamSynchronize(e->s_compute));
     BD_CHECK(e, cudaStreamSynchronize(e->s_out));
@@ -915,7 +989,7 @@ int32_t bd_submit_host(bd_engine* e, int32_t slot, const float* samples, int64_t
     if (P == 0) return 0;
     if (!samples || !act) return fail(e, "null host buffer");
     if (ensure_slot(e, s, n, P)) return 1;
-    s.n = n; s.P = P; s.hop = hop_frames; s.want_emb = emb != nullptr;
+    s.n = n; s.P = P; s.hop = hop_frames; s.want_emb = emb != nullptr; s.has_pcm = false;
     if (route_outputs(e, s, act, emb)) return 1;
     BD_CHECK(e, cudaMemcpyAsync(s.d_in, samples, n * sizeof(float), cudaMemcpyHostToDevice, e->s_in));
     BD_CHECK(e, cudaEventRecord(s.ev_in, e->s_in));
@@ -928,13 +1002,17 @@ int32_t bd_wait(bd_engine* e, int32_t slot) {
     if (!e) return 1;
     cudaEvent_t ev = nullptr;
     {
-        std::lock_guard<std::recursive_mutex> lk(e->mu);
+        std::unique_lock<std::recursive_mutex> lk(e->mu);
         if (slot < 0 || slot >= static_cast<int>(e->slots.size())) return fail(e, "slot out of range");
         Slot& s = e->slots[slot];
         if (s.state == 0) return 0;
         BD_CHECK(e, cudaSetDevice(e->device));
-        if (s.state == 1 && flush_pending(e)) return 1;
-        if (s.state != 2) return fail(e, "slot was released by a failed launch");
+        if (s.state == 1) {
+            // not launched yet: the dispatcher takes it as soon as the GPU has room; without auto-flush, ask for it
+            if (!e->auto_flush) { e->flush_req = true; e->cv_work.notify_one(); }
+            e->cv_launched.wait(lk, [&] { return e->slots[slot].state != 1 || e->stop; });
+        }
+        if (s.state != 2) return fail(e, e->last_error.empty() ? "slot was released by a failed launch" : e->last_error);
         ev = s.ev_out;
     }
     const cudaError_t we = cudaEventSynchronize(ev);        // outside the lock: the other thread keeps submitting
@@ -1212,11 +1290,8 @@ int32_t bd_submit_pcm_host(bd_engine* e, int32_t slot, const void* pcm, int32_t 
     if (route_outputs(e, s, act, emb)) return 1;
     if (n_frames > 0) BD_CHECK(e, cudaMemcpyAsync(s.d_pcm, pcm, pcm_bytes, cudaMemcpyHostToDevice, e->s_in));
     BD_CHECK(e, cudaEventRecord(s.ev_in, e->s_in));
-    // downmix + resample to the slot's 16 kHz buffer right away (stream order: behind whatever batch is running); the
-    // CNN pass itself is launched with the other pending chunks
-    BD_CHECK(e, cudaStreamWaitEvent(e->s_compute, s.ev_in, 0));
-    if (run_resample(e, r, s.d_pcm, fmt, channels, n_frames, s.d_in, n, e->s_compute)) return 1;
-    BD_CHECK(e, cudaEventRecord(s.ev_in, e->s_compute));
+    // downmix + resample to the slot's 16 kHz buffer run at the head of the pass that takes the chunk (launch_group)
+    s.has_pcm = true; s.pcm_fmt = fmt; s.pcm_channels = channels; s.pcm_rate = src_rate; s.pcm_frames = n_frames;
     s.state = 1;
     e->pending.push_back(slot);
     return maybe_flush(e);
