@@ -18,7 +18,7 @@ from . import weights as W
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libbuzzdetect_b200.so")
 
-PRECISION = {"fp32": 0, "fp32_simt": 0, "fp16": 1, "fp16x1": 1, "fp16x3": 3}
+PRECISION = {"fp32": 0, "fp32_simt": 0, "fp16": 1, "fp16x1": 1, "fp16f8": 2, "fp16x3": 3}
 DEFAULT_PRECISION = os.environ.get("BUZZ_B200_PRECISION", "fp16x3")
 
 N_LAYERS = 14

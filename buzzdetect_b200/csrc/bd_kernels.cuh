@@ -63,6 +63,7 @@ cudaError_t launch_conv1_dw2(const float* logmel, int hop_frames, int P, const f
 // out_mode 0: float32 plane `out_f32` [P*Ho*Wo, C]
 // out_mode 1: fp16 hi plane only            (single-pass tensor-core GEMM operand)
 // out_mode 2: fp16 hi + lo planes, x ~= hi + lo  (3-product split GEMM operand)
+// out_mode 3: fp16 hi plane + e5m2 correction plane at out_lo (unsigned char [M, 2C]; fp16 + fp8 plan, C % 64 == 0)
 cudaError_t launch_depthwise(const float* in, int P, int H, int W, int C, int stride, const float* w9xC,
                              const float* bC, int out_mode, float* out_f32, __half* out_hi, __half* out_lo,
                              cudaStream_t stream);
@@ -78,7 +79,9 @@ cudaError_t launch_pool_head(const float* y, int P, int rows_per_patch, const fl
 struct PwGemmPlan {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     CUtensorMap b64_hi, b64_lo;   // the same weight planes in 64-row boxes (sep_fused3_kernel's 16 KB ring slots)
-    int M_max, N, K, block_n, nsplit;
+    CUtensorMap a_c8, b_c8;       // nsplit == 2 ("fp16f8"): e5m2 correction planes [rows, 2K] bytes, per 64-channel k-block
+                                  // A: [a_lo 2^11 (64) | a_hi (64)], W: [w_hi 2^-11 (64) | w_lo (64)]
+    int M_max, N, K, block_n, nsplit;   // nsplit: 1 = fp16, 3 = fp16 hi/lo x3, 2 = fp16 + fp8 corrections
     float out_scale;   // accumulators are multiplied by this before the bias (weights are stored pre-scaled by 1/out_scale)
 };
 cudaError_t pw_gemm_init_device();
@@ -87,6 +90,10 @@ cudaError_t pw_gemm_init_device();
 cudaError_t pw_gemm_make_plan(PwGemmPlan* plan, const __half* a_hi, const __half* a_lo, int M_max, int K,
                               const __half* b_hi, const __half* b_lo, int N, int nsplit, int block_n,
                               float out_scale, const char** err);
+// nsplit == 2: a_lo / b_lo point at the e5m2 planes (unsigned char [rows, 2K]); K must be a multiple of 64.
+// The weight side of the fp16 + fp8 plan: hi = fp16(w * scale), c8 row = per k-block [e5m2(hi 2^-11) | e5m2(w*scale - hi)].
+float split_weights_f16f8(const float* w, size_t rows, size_t K, __half* hi, unsigned char* c8);
+bool encode_kmajor_u8_map(CUtensorMap* map, const void* ptr, int rows, int row_bytes, int box_rows);
 // Split float32 weights into fp16 hi/lo planes after scaling by a power of two chosen so that max|w| lands in
 // [512,1024): the lo plane then stays in fp16's NORMAL range (unscaled 1x1 weights are ~0.05, their lo parts would be
 // subnormal and carry only ~1e-6 relative precision).  Returns the inverse scale for PwGemmPlan::out_scale.

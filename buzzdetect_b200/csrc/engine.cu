@@ -15,12 +15,15 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
 #include <string>
 #include <tuple>
 #include <vector>
+
+#include <cuda_fp8.h>
 
 #include "../../include/buzzdetect_b200.h"
 #include "bd_kernels.cuh"
@@ -39,6 +42,7 @@ struct LayerDev {
     __half* w_hi = nullptr;         // [cout,cin] fp16 planes (tensor-core modes)
     __half* w_lo = nullptr;
     PwGemmPlan plan;
+    int nsplit = 3;                 // operand plan of this layer's pointwise product: 1 fp16, 3 fp16 hi/lo x3, 2 fp16 + fp8
     bool late = false;              // pointwise runs in the late phase
     bool fused = false;             // depthwise computed inside the pointwise GEMM (sep_fused_kernel)
     bool fused_v3 = false;          // ... by sep_fused3_kernel (TMA-staged depthwise input)
@@ -70,6 +74,7 @@ struct Slot {
     int64_t pcm_frames = 0;
     cudaEvent_t ev_in = nullptr, ev_comp = nullptr, ev_out = nullptr;
     int state = 0;                  // 0 free, 1 pending (input on its way, compute not enqueued), 2 launched
+    bool arrived = false;           // dispatcher: the input copy has completed
 };
 
 struct GraphKey {
@@ -108,7 +113,7 @@ struct bd_engine {
     bool l12_v2 = false;                  // ... using the warp-specialised l12_fused2_kernel
     bool cta_pairs = false;               // sep_fused3 with cta_group::2 MMAs where it applies (BD_FUSE_PAIR)
     const void* dbg_ptr = nullptr;        // bd_debug_stage: where the requested stage's output lives
-    bool dbg_planes = false;
+    int dbg_planes = 0;                   // 0: float32; else the producing layer's operand plan (1, 2, 3)
     size_t dbg_plane_off = 0;
     std::vector<Slot> slots;
     std::vector<int> pending;             // slots submitted but not yet launched, in submission order
@@ -255,7 +260,12 @@ int enqueue_chunk(bd_engine* e, const FrontJob& job, int hop_frames, float* d_ac
     const int prec = e->precision;
     const int dw_mode = prec == BD_PRECISION_FP32_SIMT ? 0 : (prec == BD_PRECISION_FP16X1 ? 1 : 2);
     const int first_late = e->first_late;
-    auto stop_at = [&](int stage, const void* ptr, bool planes, size_t plane_off) {
+    auto dw_mode_of = [&](int L) {                      // output format of the depthwise kernel feeding layer L's GEMM
+        if (prec == BD_PRECISION_FP32_SIMT) return 0;
+        const int ns = e->layers[L].nsplit;
+        return ns == 1 ? 1 : (ns == 2 ? 3 : 2);
+    };
+    auto stop_at = [&](int stage, const void* ptr, int planes, size_t plane_off) {
         if (stop_stage != stage) return false;
         e->dbg_ptr = ptr; e->dbg_planes = planes; e->dbg_plane_off = plane_off;
         return true;
@@ -268,10 +278,11 @@ int enqueue_chunk(bd_engine* e, const FrontJob& job, int hop_frames, float* d_ac
         __half* ohi = reinterpret_cast<__half*>(H) + row_off * l.d.cin;
         __half* olo = reinterpret_cast<__half*>(H + plane) + row_off * l.d.cin;
         if (do_dw) {
-            BD_CHECK(e, launch_depthwise(in, np, l.d.h_in, l.d.w_in, l.d.cin, l.d.stride, l.dw_w, l.dw_b, dw_mode, o32,
+            const int dwm = dw_mode_of(L);
+            BD_CHECK(e, launch_depthwise(in, np, l.d.h_in, l.d.w_in, l.d.cin, l.d.stride, l.dw_w, l.dw_b, dwm, o32,
                                          ohi, olo, st));
             mark(e, CAT_DW + L - 1, st);
-            if (stop_at(2 * L, H + (dw_mode == 0 ? 4 : 2) * row_off * l.d.cin, dw_mode != 0, plane)) return 2;
+            if (stop_at(2 * L, H + (dwm == 0 ? 4 : 2) * row_off * l.d.cin, dwm == 0 ? 0 : l.nsplit, plane)) return 2;
         }
         if (do_pw) {
             const int M = np * l.h_out * l.w_out;
@@ -281,7 +292,7 @@ int enqueue_chunk(bd_engine* e, const FrontJob& job, int hop_frames, float* d_ac
                 BD_CHECK(e, launch_pw_gemm(l.plan, l.b, out, M, e->num_sms, st));
             }
             mark(e, CAT_PW + L - 1, st);
-            if (stop_at(2 * L + 1, out, false, 0)) return 2;
+            if (stop_at(2 * L + 1, out, 0, 0)) return 2;
         }
         return 0;
     };
@@ -295,7 +306,7 @@ int enqueue_chunk(bd_engine* e, const FrontJob& job, int hop_frames, float* d_ac
                                          e->num_sms, st));
         mark(e, CAT_PW + L - 1, st);
         if (stop_stage == 2 * L) { e->last_error = "stage is fused away (depthwise output stays in shared memory)"; return 1; }
-        if (stop_at(2 * L + 1, out, false, 0)) return 2;
+        if (stop_at(2 * L + 1, out, 0, 0)) return 2;
         return 0;
     };
     for (int64_t big = 0; big < P; big += e->S2) {
@@ -304,7 +315,7 @@ int enqueue_chunk(bd_engine* e, const FrontJob& job, int hop_frames, float* d_ac
         {
             if (run_frontend(e, job, big, nb, hop_frames, st)) return 1;
             mark(e, CAT_FRONTEND, st);
-            if (stop_at(0, e->d_logmel, false, 0)) return 0;
+            if (stop_at(0, e->d_logmel, 0, 0)) return 0;
         }
         const LayerDev& lb = e->layers[first_late];          // boundary layer: its pointwise output lives in F_late
         // ---------------- early phase
@@ -329,7 +340,7 @@ int enqueue_chunk(bd_engine* e, const FrontJob& job, int hop_frames, float* d_ac
                     e->last_error = "stage is fused away (layers 1-2 run as one kernel)";
                     return 1;
                 }
-                if (stop_at(3, cur, false, 0)) return 0;
+                if (stop_at(3, cur, 0, 0)) return 0;
                 L0 = 2;
             } else if (e->fuse_conv1 && !e->layers[1].fused) {
                 // layer 1 + layer-2 depthwise in one kernel, then layer-2 pointwise
@@ -339,14 +350,14 @@ int enqueue_chunk(bd_engine* e, const FrontJob& job, int hop_frames, float* d_ac
                                              reinterpret_cast<__half*>(e->d_H_early + e->H_early_plane_bytes), st));
                 mark(e, CAT_CONV1, st);
                 if (stop_stage == 1) { e->last_error = "stage is fused away (layer-1 output stays in shared memory)"; return 1; }
-                if (stop_at(2, e->d_H_early, dw_mode != 0, e->H_early_plane_bytes)) return 0;
+                if (stop_at(2, e->d_H_early, dw_mode == 0 ? 0 : l2.nsplit, e->H_early_plane_bytes)) return 0;
                 const int rc2 = unfused(1, nullptr, ns, e->d_H_early, e->H_early_plane_bytes, 0, cur, false, true);
                 if (rc2) return rc2 == 2 ? 0 : rc2;
                 L0 = 2;
             } else {
                 BD_CHECK(e, launch_conv1(lm0, hop_frames, ns, l1.w, l1.b, cur, st));
                 mark(e, CAT_CONV1, st);
-                if (stop_at(1, cur, false, 0)) return 0;
+                if (stop_at(1, cur, 0, 0)) return 0;
             }
             for (int L = L0; L < first_late; ++L) {
                 int rc;
@@ -578,7 +589,7 @@ int launch_pending(bd_engine* e, bool only_arrived) {
             Slot& s = e->slots[e->pending[pos]];
             if (s.hop != hop) break;
             if (!group.empty() && g + tail_slots + s.P > e->S2) break;
-            if (only_arrived && !group.empty() && cudaEventQuery(s.ev_in) != cudaSuccess) { cudaGetLastError(); break; }
+            if (only_arrived && !s.arrived) break;
             g += (group.empty() ? 0 : tail_slots) + s.P;
             group.push_back(e->pending[pos]);
             outs.push_back(SlotOut{s.dst_act, s.want_emb ? s.dst_emb : nullptr});
@@ -599,6 +610,13 @@ int launch_pending(bd_engine* e, bool only_arrived) {
 
 int flush_pending(bd_engine* e) { return launch_pending(e, false); }
 
+// Dispatcher policy (auto mode).  `arrived` = pending chunks, in order, whose input has reached the device.
+//   * nothing in the stream            -> launch what has arrived at once (a lone chunk is not kept waiting);
+//   * one pass running                 -> queue the next pass behind it only when enough has arrived to fill the GPU
+//                                         (coalesce_target patches), otherwise keep collecting until the pass ends;
+//   * two passes in the stream         -> wait.
+// So an input-bound caller gets every chunk computed as soon as it lands, and a compute-bound one gets passes that
+// grow towards late_patches -- without either having to call anything.
 void dispatcher_main(bd_engine* e) {
     cudaSetDevice(e->device);
     std::unique_lock<std::recursive_mutex> lk(e->mu);
@@ -610,27 +628,29 @@ void dispatcher_main(bd_engine* e) {
             launch_pending(e, false);
             continue;
         }
-        // at most two passes in the stream: the one running and the one queued behind it
-        cudaEvent_t gate = e->ev_pass[e->pass_seq & 1];
-        if (e->pass_seq >= 2 && cudaEventQuery(gate) == cudaErrorNotReady) {
-            cudaGetLastError();
-            lk.unlock();
-            cudaEventSynchronize(gate);
-            lk.lock();
-            continue;                               // re-evaluate: more chunks may have been queued meanwhile
+        int n_arr = 0;
+        int64_t arrived = 0;
+        for (int si : e->pending) {
+            Slot& s = e->slots[si];
+            if (!s.arrived) {
+                if (cudaEventQuery(s.ev_in) != cudaSuccess) { cudaGetLastError(); break; }
+                s.arrived = true;
+            }
+            ++n_arr;
+            arrived += s.P;
         }
+        int inflight = 0;
+        for (int back = 1; back <= 2 && back <= e->pass_seq; ++back)
+            if (cudaEventQuery(e->ev_pass[(e->pass_seq - back) & 1]) == cudaErrorNotReady) ++inflight;
         cudaGetLastError();
-        // the first pending chunk must have reached the device (a pass that waits for PCIe blocks the ones behind it)
-        cudaEvent_t first = e->slots[e->pending[0]].ev_in;
-        if (cudaEventQuery(first) == cudaErrorNotReady) {
-            cudaGetLastError();
+        const bool go = n_arr > 0 && (inflight == 0 || (inflight == 1 && arrived >= e->coalesce_target));
+        if (go) {
+            launch_pending(e, true);
+        } else {
             lk.unlock();
-            cudaEventSynchronize(first);
+            std::this_thread::sleep_for(std::chrono::microseconds(15));
             lk.lock();
-            continue;
         }
-        cudaGetLastError();
-        launch_pending(e, true);
     }
 }
 
@@ -728,8 +748,8 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
     if (!cfg || !w || !out) return set_err("null argument");
     *out = nullptr;
     if (cfg->precision != BD_PRECISION_FP32_SIMT && cfg->precision != BD_PRECISION_FP16X1 &&
-        cfg->precision != BD_PRECISION_FP16X3)
-        return set_err("precision must be 0 (fp32 SIMT), 1 (fp16) or 3 (fp16 x3 split)");
+        cfg->precision != BD_PRECISION_FP16X3 && cfg->precision != BD_PRECISION_FP16F8)
+        return set_err("precision must be 0 (fp32 SIMT), 1 (fp16), 2 (fp16 + fp8 corrections) or 3 (fp16 x3 split)");
     if (w->n_classes < 1 || w->n_classes > kMaxClasses) return set_err("n_classes out of range");
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -883,12 +903,21 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
 
     // ---- tensor-core operands: weight planes + TMA descriptors
     if (e->precision != BD_PRECISION_FP32_SIMT) {
-        const int nsplit = e->precision == BD_PRECISION_FP16X3 ? 3 : 1;
         for (int L = 1; L < BD_N_LAYERS; ++L) {
             LayerDev& l = e->layers[L];
+            // operand plan per layer.  "fp16f8": the fp16 + fp8 plan where a kernel implements it (sep_fused3 and the
+            // depthwise + GEMM pairs, K a multiple of 64); the HBM-bound early layers keep the x3 split
+            int nsplit = e->precision == BD_PRECISION_FP16X1 ? 1 : 3;
+            if (e->precision == BD_PRECISION_FP16F8 && l.d.cin % 64 == 0 && (l.fused_v3 || !l.fused)) nsplit = 2;
+            l.nsplit = nsplit;
             const size_t nw = static_cast<size_t>(l.d.cout) * l.d.cin;
             std::vector<__half> hi(nw), lo(nw);
-            const float out_scale = split_weights_f16(w->folded + l.d.w, nw, hi.data(), lo.data()) / kActScale;
+            float out_scale;
+            if (nsplit == 2)
+                out_scale = split_weights_f16f8(w->folded + l.d.w, l.d.cout, l.d.cin, hi.data(),
+                                                reinterpret_cast<unsigned char*>(lo.data())) / kActScale;
+            else
+                out_scale = split_weights_f16(w->folded + l.d.w, nw, hi.data(), lo.data()) / kActScale;
             BD_CREATE(cudaMalloc(&l.w_hi, nw * sizeof(__half)));
             BD_CREATE(cudaMalloc(&l.w_lo, nw * sizeof(__half)));
             BD_CREATE(cudaMemcpy(l.w_hi, hi.data(), nw * sizeof(__half), cudaMemcpyHostToDevice));
@@ -917,7 +946,7 @@ int32_t bd_engine_create(const bd_config* cfg, const bd_weights* w, bd_engine** 
     e->slots.resize(ns);
     for (int i = 0; i < 2; ++i) BD_CREATE(cudaEventCreateWithFlags(&e->ev_batch_out[i], cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) BD_CREATE(cudaEventCreateWithFlags(&e->ev_pass[i], cudaEventDisableTiming));
-    e->coalesce_target = std::max<int64_t>(1, static_cast<int64_t>(e->S2) * 3 / 4);
+    e->coalesce_target = std::max<int64_t>(1, static_cast<int64_t>(e->S2) / 2);
     if (const char* ct = getenv("BD_COALESCE_PATCHES")) e->coalesce_target = std::max<int64_t>(1, atoll(ct));
     for (auto& s : e->slots) {
         BD_CREATE(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
@@ -989,7 +1018,7 @@ int32_t bd_submit_host(bd_engine* e, int32_t slot, const float* samples, int64_t
     if (P == 0) return 0;
     if (!samples || !act) return fail(e, "null host buffer");
     if (ensure_slot(e, s, n, P)) return 1;
-    s.n = n; s.P = P; s.hop = hop_frames; s.want_emb = emb != nullptr; s.has_pcm = false;
+    s.n = n; s.P = P; s.hop = hop_frames; s.want_emb = emb != nullptr; s.has_pcm = false; s.arrived = false;
     if (route_outputs(e, s, act, emb)) return 1;
     BD_CHECK(e, cudaMemcpyAsync(s.d_in, samples, n * sizeof(float), cudaMemcpyHostToDevice, e->s_in));
     BD_CHECK(e, cudaEventRecord(s.ev_in, e->s_in));
@@ -1286,7 +1315,7 @@ int32_t bd_submit_pcm_host(bd_engine* e, int32_t slot, const void* pcm, int32_t 
     bd_engine::Resampler ident{1, 1, 1, nullptr};
     bd_engine::Resampler* r = &ident;
     if (src_rate != 16000 && get_resampler(e, src_rate, &r)) return 1;
-    s.n = n; s.P = P; s.hop = hop_frames; s.want_emb = emb != nullptr;
+    s.n = n; s.P = P; s.hop = hop_frames; s.want_emb = emb != nullptr; s.arrived = false;
     if (route_outputs(e, s, act, emb)) return 1;
     if (n_frames > 0) BD_CHECK(e, cudaMemcpyAsync(s.d_pcm, pcm, pcm_bytes, cudaMemcpyHostToDevice, e->s_in));
     BD_CHECK(e, cudaEventRecord(s.ev_in, e->s_in));
@@ -1440,7 +1469,7 @@ int32_t bd_debug_stage(bd_engine* e, const float* samples, int64_t n, int32_t ho
     if (rc == 0) {
         int64_t count = 0;
         const void* src = e->dbg_ptr;
-        const bool planes = e->dbg_planes;
+        const int planes = e->dbg_planes;
         const size_t plane_off = e->dbg_plane_off;
         if (stage == 0) {
             count = (static_cast<int64_t>(P - 1) * hop_frames + kPatchFrames) * kMel;
@@ -1453,17 +1482,27 @@ int32_t bd_debug_stage(bd_engine* e, const float* samples, int64_t n, int32_t ho
         if (src == nullptr) rc = fail(e, "debug stage was not reached");
         if (rc == 0 && count > out_capacity) {
             rc = fail(e, "debug stage output buffer too small");
-        } else if (rc == 0 && !planes) {
+        } else if (rc == 0 && planes == 0) {
             cudaError_t me = cudaMemcpy(out, src, count * sizeof(float), cudaMemcpyDeviceToHost);
             if (me != cudaSuccess) rc = fail(e, cudaGetErrorString(me));
         } else if (rc == 0) {
             std::vector<__half> hi(count), lo(count);
             cudaMemcpy(hi.data(), src, count * sizeof(__half), cudaMemcpyDeviceToHost);
-            if (e->precision == BD_PRECISION_FP16X3)
+            if (planes != 1)
                 cudaMemcpy(lo.data(), static_cast<const unsigned char*>(src) + plane_off, count * sizeof(__half),
                            cudaMemcpyDeviceToHost);
-            for (int64_t i = 0; i < count; ++i)      // undo the 2^-4 operand scale (see bd_engine_create)
-                out[i] = (__half2float(hi[i]) + (e->precision == BD_PRECISION_FP16X3 ? __half2float(lo[i]) : 0.f)) / kActScale;
+            const LayerDev& ld = e->layers[stage / 2];
+            const unsigned char* c8 = reinterpret_cast<const unsigned char*>(lo.data());
+            for (int64_t i = 0; i < count; ++i) {    // undo the 2^-4 operand scale (see bd_engine_create)
+                float v = __half2float(hi[i]);
+                if (planes == 3) v += __half2float(lo[i]);
+                if (planes == 2) {                   // e5m2 plane: per 64-channel k-block [lo * 2^11 | hi]
+                    const int64_t row = i / ld.d.cin, c = i % ld.d.cin;
+                    const __half_raw hr = __nv_cvt_fp8_to_halfraw(c8[row * 2 * ld.d.cin + (c / 64) * 128 + (c % 64)], __NV_E5M2);
+                    v += __half2float(__half(hr)) / 2048.f;
+                }
+                out[i] = v / kActScale;
+            }
         }
         if (rc == 0 && n_out) *n_out = count;
     }

@@ -266,6 +266,15 @@ __global__ void __launch_bounds__(256) depthwise_kernel(const float* __restrict_
                         __halves2half2(half_sat(a.z - __half2float(h2)), half_sat(a.w - __half2float(h3)))};
                     *reinterpret_cast<uint2*>(out_lo + o) = *reinterpret_cast<uint2*>(lp);
                 }
+                if (OUT_MODE == 3) {
+                    // fp16 + fp8 plan: second plane = e5m2 bytes [M, 2C], per 64-channel k-block [lo * 2^11 | hi]
+                    const float f0 = __half2float(h0), f1 = __half2float(h1), f2 = __half2float(h2), f3 = __half2float(h3);
+                    const int c = c4 * 4;
+                    unsigned char* row = reinterpret_cast<unsigned char*>(out_lo) + (pix0 + r) * 2 * C + (c >> 6) * 128 + (c & 63);
+                    *reinterpret_cast<uint32_t*>(row) = pack_e5m2x4((a.x - f0) * kF8LoScale, (a.y - f1) * kF8LoScale,
+                                                                    (a.z - f2) * kF8LoScale, (a.w - f3) * kF8LoScale);
+                    *reinterpret_cast<uint32_t*>(row + 64) = pack_e5m2x4(f0, f1, f2, f3);
+                }
             }
         }
     }
@@ -499,12 +508,12 @@ cudaError_t launch_depthwise(const float* in, int P, int H, int W, int C, int st
                              int out_mode, float* out_f32, __half* out_hi, __half* out_lo, cudaStream_t stream) {
     if (P <= 0) return cudaSuccess;
     if ((C & 3) || (stride != 1 && stride != 2) || (stride == 2 && ((H | W) & 1))) return cudaErrorInvalidValue;
-    if (out_mode < 0 || out_mode > 2) return cudaErrorInvalidValue;
+    if (out_mode < 0 || out_mode > 3 || (out_mode == 3 && C % 64 != 0)) return cudaErrorInvalidValue;
     const int Wo = W / stride;
     const int R = (Wo % 4 == 0) ? 4 : ((Wo % 2 == 0) ? 2 : 1);
     const unsigned c4 = static_cast<unsigned>(C / 4), wsn = static_cast<unsigned>(Wo / R);
     if ((c4 & (c4 - 1)) || (wsn & (wsn - 1))) return cudaErrorInvalidValue;      // shift/mask indexing (see kernel)
-    const bool two_rows = ((H / stride) % 2 == 0) && (R == 4 || R == 2) && dw_two_rows_enabled();
+    const bool two_rows = ((H / stride) % 2 == 0) && (R == 4 || R == 2) && dw_two_rows_enabled() && out_mode != 3;
     const long long items = static_cast<long long>(H / stride) / (two_rows ? 2 : 1) * wsn * c4;
     const long long blocks = static_cast<long long>(P) * ((items + 255) / 256);
     if (blocks >= (1LL << 31)) return cudaErrorInvalidValue;
@@ -530,6 +539,7 @@ cudaError_t launch_depthwise(const float* in, int P, int H, int W, int C, int st
     do {                                           \
         if (out_mode == 0) BD_DW(S, RR, 0);        \
         else if (out_mode == 1) BD_DW(S, RR, 1);   \
+        else if (out_mode == 3) BD_DW(S, RR, 3);   \
         else BD_DW(S, RR, 2);                      \
     } while (0)
     if (stride == 1) {

@@ -21,6 +21,7 @@
 // l12_fused_kernel: layers 1+2 behind CTA-wide barriers), kept selectable through fuse_mask and parity-tested; the
 // default plan uses sep_fused_sm100.cu and l12_fused_sm100.cu instead.
 #include <cmath>
+#include <cuda_fp8.h>
 
 #include "bd_common.cuh"
 #include "bd_kernels.cuh"
@@ -109,11 +110,13 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char* st = smem + stage * Cfg::kStageBytes;
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    // second planes: fp16 lo, or (NSPLIT = 2) the e5m2 correction planes, 128 bytes per k-block
+                    constexpr int kc2 = NSPLIT == 2 ? 2 : 1;
                     tma_load_2d(st, &map_a_hi, &full_bar[stage], kb * kBK, m_blk * kBM);
-                    if (NSPLIT > 1) tma_load_2d(st + Cfg::kATile, &map_a_lo, &full_bar[stage], kb * kBK, m_blk * kBM);
+                    if (NSPLIT > 1) tma_load_2d(st + Cfg::kATile, &map_a_lo, &full_bar[stage], kb * kBK * kc2, m_blk * kBM);
                     unsigned char* sb = st + Cfg::kPlanes * Cfg::kATile;
                     tma_load_2d(sb, &map_b_hi, &full_bar[stage], kb * kBK, n_blk * BN);
-                    if (NSPLIT > 1) tma_load_2d(sb + Cfg::kBTile, &map_b_lo, &full_bar[stage], kb * kBK, n_blk * BN);
+                    if (NSPLIT > 1) tma_load_2d(sb + Cfg::kBTile, &map_b_lo, &full_bar[stage], kb * kBK * kc2, n_blk * BN);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -143,11 +146,19 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         const uint64_t da_hi = umma_desc_k128(a_hi + koff);
                         const uint64_t db_hi = umma_desc_k128(b_hi + koff);
                         umma_f16_ss(d_tmem, da_hi, db_hi, idesc, (kb | k) != 0 ? 1u : 0u);
-                        if (NSPLIT > 1) {
+                        if (NSPLIT == 3) {
                             const uint64_t da_lo = umma_desc_k128(a_lo + koff);
                             const uint64_t db_lo = umma_desc_k128(b_lo + koff);
                             umma_f16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
                             umma_f16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
+                        }
+                    }
+                    if (NSPLIT == 2) {
+                        constexpr uint32_t idesc8 = umma_idesc_e5m2(kBM, BN);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t koff = static_cast<uint32_t>(k) * 32u;  // 32 e5m2 = 32 bytes along K
+                            umma_f8_ss(d_tmem, umma_desc_k128(a_lo + koff), umma_desc_k128(b_lo + koff), idesc8, 1u);
                         }
                     }
                     umma_commit(&empty_bar[stage]);          // smem slot reusable once these MMAs retire
@@ -717,6 +728,19 @@ bool encode_2d_f16(CUtensorMap* map, const void* ptr, int rows, int cols, int bo
     return r == CUDA_SUCCESS;
 }
 
+bool encode_2d_u8(CUtensorMap* map, const void* ptr, int rows, int row_bytes, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr || row_bytes % 128 != 0) return false;
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(row_bytes), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(row_bytes)};
+    cuuint32_t box[2] = {128u, static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 template <int BN, int NSPLIT>
 cudaError_t set_attr() {
     return cudaFuncSetAttribute(pw_gemm_kernel<BN, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -728,7 +752,7 @@ cudaError_t launch_t(const PwGemmPlan& p, const float* bias, float* C, int M, in
     const int tiles = ((M + kBM - 1) / kBM) * (p.N / BN);
     const int grid = tiles < num_sms ? tiles : num_sms;
     pw_gemm_kernel<BN, NSPLIT><<<grid, kGemmThreads, GemmCfg<BN, NSPLIT>::kSmemBytes, stream>>>(
-        p.a_hi, p.a_lo, p.b_hi, p.b_lo, bias, C, M, p.N, p.K, p.out_scale);
+        p.a_hi, NSPLIT == 2 ? p.a_c8 : p.a_lo, p.b_hi, NSPLIT == 2 ? p.b_c8 : p.b_lo, bias, C, M, p.N, p.K, p.out_scale);
     return cudaGetLastError();
 }
 
@@ -768,6 +792,34 @@ bool encode_kmajor_f16_map(CUtensorMap* map, const void* ptr, int rows, int cols
     return encode_2d_f16(map, ptr, rows, cols, box_rows);
 }
 
+bool encode_kmajor_u8_map(CUtensorMap* map, const void* ptr, int rows, int row_bytes, int box_rows) {
+    return encode_2d_u8(map, ptr, rows, row_bytes, box_rows);
+}
+
+float split_weights_f16f8(const float* w, size_t rows, size_t K, __half* hi, unsigned char* c8) {
+    const size_t n = rows * K;
+    float mx = 0.f;
+    for (size_t i = 0; i < n; ++i) mx = fmaxf(mx, fabsf(w[i]));
+    int ex = 0;
+    float scale = 1.f;
+    if (mx > 0.f && std::isfinite(mx)) {
+        std::frexp(mx, &ex);
+        scale = std::ldexp(1.0f, 10 - ex);    // mx*scale in [512,1024), as in split_weights_f16
+    }
+    for (size_t r = 0; r < rows; ++r) {
+        for (size_t k = 0; k < K; ++k) {
+            const float v = w[r * K + k] * scale;
+            const __half h = __float2half_rn(v);
+            hi[r * K + k] = h;
+            const float hf = __half2float(h);
+            unsigned char* row = c8 + r * 2 * K + (k / 64) * 128 + (k % 64);
+            row[0] = static_cast<unsigned char>(__nv_cvt_float_to_fp8(hf / 2048.f, __NV_SATFINITE, __NV_E5M2));
+            row[64] = static_cast<unsigned char>(__nv_cvt_float_to_fp8(v - hf, __NV_SATFINITE, __NV_E5M2));
+        }
+    }
+    return 1.0f / scale;
+}
+
 bool encode_store_map_f32(CUtensorMap* map, float* ptr, long long rows, int cols, int box_rows) {
     TensorMapEncodeFn fn = tensor_map_encode_fn();
     if (fn == nullptr || cols % 32 != 0 || rows < 1 || box_rows < 8 || box_rows % 8) return false;
@@ -803,6 +855,9 @@ cudaError_t pw_gemm_init_device() {
     if ((e = set_attr<64, 1>()) != cudaSuccess) return e;
     if ((e = set_attr<128, 1>()) != cudaSuccess) return e;
     if ((e = set_attr<256, 1>()) != cudaSuccess) return e;
+    if ((e = set_attr<64, 2>()) != cudaSuccess) return e;
+    if ((e = set_attr<128, 2>()) != cudaSuccess) return e;
+    if ((e = set_attr<256, 2>()) != cudaSuccess) return e;
     if ((e = set_attr<64, 3>()) != cudaSuccess) return e;
     if ((e = set_attr<128, 3>()) != cudaSuccess) return e;
     if ((e = set_attr<256, 3>()) != cudaSuccess) return e;
@@ -861,7 +916,11 @@ cudaError_t pw_gemm_make_plan(PwGemmPlan* plan, const __half* a_hi, const __half
                               const __half* b_hi, const __half* b_lo, int N, int nsplit, int block_n,
                               float out_scale, const char** err) {
     *err = nullptr;
-    if (nsplit != 1 && nsplit != 3) { *err = "nsplit must be 1 or 3"; return cudaErrorInvalidValue; }
+    if (nsplit != 1 && nsplit != 3 && nsplit != 2) { *err = "nsplit must be 1, 2 or 3"; return cudaErrorInvalidValue; }
+    if (nsplit == 2 && (K % 64 != 0 || a_lo == nullptr || b_lo == nullptr)) {
+        *err = "the fp16 + fp8 plan needs K % 64 == 0 and both e5m2 planes";
+        return cudaErrorInvalidValue;
+    }
     if (K % 8 != 0) { *err = "K must be a multiple of 8 (16-byte TMA row stride)"; return cudaErrorInvalidValue; }
     int bn = block_n;
     if (bn <= 0) bn = N % 128 == 0 ? 128 : 64;
@@ -875,6 +934,10 @@ cudaError_t pw_gemm_make_plan(PwGemmPlan* plan, const __half* a_hi, const __half
         *err = "cuTensorMapEncodeTiled failed";
         return cudaErrorUnknown;
     }
+    if (nsplit == 2 && (!encode_2d_u8(&plan->a_c8, a_lo, M_max, 2 * K, kBM) || !encode_2d_u8(&plan->b_c8, b_lo, N, 2 * K, bn))) {
+        *err = "cuTensorMapEncodeTiled failed (e5m2 planes)";
+        return cudaErrorUnknown;
+    }
     return cudaSuccess;
 }
 
@@ -885,6 +948,11 @@ cudaError_t launch_pw_gemm(const PwGemmPlan& p, const float* bias, float* C, int
         if (p.block_n == 64) return launch_t<64, 1>(p, bias, C, M, num_sms, stream);
         if (p.block_n == 128) return launch_t<128, 1>(p, bias, C, M, num_sms, stream);
         return launch_t<256, 1>(p, bias, C, M, num_sms, stream);
+    }
+    if (p.nsplit == 2) {
+        if (p.block_n == 64) return launch_t<64, 2>(p, bias, C, M, num_sms, stream);
+        if (p.block_n == 128) return launch_t<128, 2>(p, bias, C, M, num_sms, stream);
+        return launch_t<256, 2>(p, bias, C, M, num_sms, stream);
     }
     if (p.block_n == 64) return launch_t<64, 3>(p, bias, C, M, num_sms, stream);
     if (p.block_n == 128) return launch_t<128, 3>(p, bias, C, M, num_sms, stream);

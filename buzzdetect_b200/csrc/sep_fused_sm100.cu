@@ -93,19 +93,30 @@ __device__ __forceinline__ void tma_prefetch_4d(const void* map, int32_t c0, int
                  : "memory");
 }
 
-// hi/lo fp16 of 4 channels of one pixel -> the swizzled A tile (row = pixel, 128-byte rows, 16-byte chunks XOR row&7)
+// hi/lo fp16 of 4 channels of one pixel -> the swizzled A tile (row = pixel, 128-byte rows, 16-byte chunks XOR row&7).
+// NSPLIT = 2 ("fp16f8"): the second plane holds e5m2 bytes instead, [lo * 2^11 (64 channels) | hi (64 channels)] per row.
 template <int NSPLIT>
-__device__ __forceinline__ void store_a(uint32_t a_hi, uint32_t a_lo, uint32_t row, uint32_t chunk, uint32_t half8, float4 a) {
+__device__ __forceinline__ void store_a(uint32_t a_hi, uint32_t a_lo, uint32_t row, uint32_t chunk, uint32_t half8,
+                                        uint32_t c8chunk, uint32_t c8off, float4 a) {
     a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
-    const uint32_t off = (row >> 3) * 1024u + (row & 7u) * 128u + ((chunk ^ (row & 7u)) << 4) + half8;
+    const uint32_t rowoff = (row >> 3) * 1024u + (row & 7u) * 128u;
+    const uint32_t off = rowoff + ((chunk ^ (row & 7u)) << 4) + half8;
     const __half h0 = half_sat(a.x), h1 = half_sat(a.y);
     const __half h2 = half_sat(a.z), h3 = half_sat(a.w);
     __half2 hp[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
     sts64(a_hi + off, reinterpret_cast<uint32_t*>(hp)[0], reinterpret_cast<uint32_t*>(hp)[1]);
-    if (NSPLIT > 1) {
+    if (NSPLIT == 3) {
         __half2 lp[2] = {__halves2half2(half_sat(a.x - __half2float(h0)), half_sat(a.y - __half2float(h1))),
                          __halves2half2(half_sat(a.z - __half2float(h2)), half_sat(a.w - __half2float(h3)))};
         sts64(a_lo + off, reinterpret_cast<uint32_t*>(lp)[0], reinterpret_cast<uint32_t*>(lp)[1]);
+    }
+    if (NSPLIT == 2) {
+        const float f0 = __half2float(h0), f1 = __half2float(h1), f2 = __half2float(h2), f3 = __half2float(h3);
+        const uint32_t lo8 = pack_e5m2x4((a.x - f0) * kF8LoScale, (a.y - f1) * kF8LoScale, (a.z - f2) * kF8LoScale,
+                                         (a.w - f3) * kF8LoScale);
+        const uint32_t hi8 = pack_e5m2x4(f0, f1, f2, f3);
+        sts32u(a_lo + rowoff + ((c8chunk ^ (row & 7u)) << 4) + c8off, lo8);
+        sts32u(a_lo + rowoff + (((c8chunk + 4u) ^ (row & 7u)) << 4) + c8off, hi8);
     }
 }
 
@@ -227,13 +238,14 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
                             const int row = n0 + nb * kMmaN + cta_rank * kBNs;
                             if (leader) mbar_arrive_expect_tx(&b_full[bs], 2 * kBSlotBytes);
                             tma_load_2d_pair(dst, &map_b_hi, &b_full[bs], kb * kBK, row);
-                            if (NSPLIT > 1) tma_load_2d_pair(dst + kBSlotPlane, &map_b_lo, &b_full[bs], kb * kBK, row);
+                            if (NSPLIT > 1) tma_load_2d_pair(dst + kBSlotPlane, &map_b_lo, &b_full[bs], kb * kBK * (NSPLIT == 2 ? 2 : 1), row);
                             if (++bs == b_slots) { bs = 0; bphase ^= 1; }
                             continue;
                         }
                         mbar_arrive_expect_tx(&b_full[bs], kBSlotBytes);
                         tma_load_2d(dst, &map_b_hi, &b_full[bs], kb * kBK, n0 + nb * kBNs);
-                        if (NSPLIT > 1) tma_load_2d(dst + kBSlotPlane, &map_b_lo, &b_full[bs], kb * kBK, n0 + nb * kBNs);
+                        // second plane: the fp16 lo weights, or (NSPLIT = 2) the e5m2 plane [w_hi 2^-11 | w_lo], 128 bytes per k-block
+                        if (NSPLIT > 1) tma_load_2d(dst + kBSlotPlane, &map_b_lo, &b_full[bs], kb * kBK * (NSPLIT == 2 ? 2 : 1), n0 + nb * kBNs);
                         if (++bs == b_slots) { bs = 0; bphase ^= 1; }
                     }
                 }
@@ -331,17 +343,24 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
                                 const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
                                 if (CTA2) {
                                     umma_f16_ss_pair(d_tmem, da_hi + koff, db_hi + koff, idesc, accum);
-                                    if (NSPLIT > 1) {
+                                    if (NSPLIT == 3) {
                                         umma_f16_ss_pair(d_tmem, da_lo + koff, db_hi + koff, idesc, 1u);
                                         umma_f16_ss_pair(d_tmem, da_hi + koff, db_lo + koff, idesc, 1u);
                                     }
                                 } else {
                                     umma_f16_ss(d_tmem, da_hi + koff, db_hi + koff, idesc, accum);
-                                    if (NSPLIT > 1) {
+                                    if (NSPLIT == 3) {
                                         umma_f16_ss(d_tmem, da_lo + koff, db_hi + koff, idesc, 1u);
                                         umma_f16_ss(d_tmem, da_hi + koff, db_lo + koff, idesc, 1u);
                                     }
                                 }
+                            }
+                            if (NSPLIT == 2 && !CTA2) {
+                                // both correction products as one e5m2 contraction over the second planes (K = 128 bytes)
+                                constexpr uint32_t idesc8 = umma_idesc_e5m2(kBM, kMmaN);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_f8_ss(d_tmem, da_lo + static_cast<uint64_t>(k) * 2u, db_lo + static_cast<uint64_t>(k) * 2u, idesc8, 1u);
                             }
                             if (CTA2) umma_commit_pair(&b_empty[bs]); else umma_commit(&b_empty[bs]);
                             if (nb == kSlotsPerKb - 1) {
@@ -414,6 +433,7 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
                         sb_loaded = sb;
                     }
                     const uint32_t chunk = static_cast<uint32_t>(sb * 4 + (quad >> 1));
+                    const uint32_t c8chunk = static_cast<uint32_t>(sb * 2 + (quad >> 2)), c8off = static_cast<uint32_t>(quad & 3) << 2;
                     mbar_wait_sleepy(&in_full[is], iphase);
                     const uint32_t tile = in_ring_u32 + static_cast<uint32_t>(is * prm.in_stride);
                     const uint32_t part_row = static_cast<uint32_t>(part * prm.rows_per_part);
@@ -450,7 +470,7 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
                         for (int o = 0; o < 2; ++o)
 #pragma unroll
                             for (int r = 0; r < BWc; ++r)
-                                store_a<NSPLIT>(a_hi, a_lo, row0 + static_cast<uint32_t>(o * Wo + r), chunk, half8, acc[o][r]);
+                                store_a<NSPLIT>(a_hi, a_lo, row0 + static_cast<uint32_t>(o * Wo + r), chunk, half8, c8chunk, c8off, acc[o][r]);
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&in_empty[is]);               // box consumed (release orders the reads)
@@ -555,7 +575,7 @@ template <int NSPLIT, int STRIDE, int NACC, bool NOHALO>
 cudaError_t launch_f3_t(const CUtensorMap& map_in, const CUtensorMap& map_c, const CUtensorMap& map_c8, const BiasParam& bp,
                         const PwGemmPlan& p, const F3Params& prm, int smem_bytes, int grid, cudaStream_t stream) {
     sep_fused3_kernel<NSPLIT, STRIDE, NACC, NOHALO, false><<<grid, kF3Threads, smem_bytes, stream>>>(
-        map_in, p.b_hi, p.b_lo, map_c, map_c8, bp, prm);
+        map_in, p.b_hi, NSPLIT == 2 ? p.b_c8 : p.b_lo, map_c, map_c8, bp, prm);
     return cudaGetLastError();
 }
 
@@ -659,6 +679,8 @@ cudaError_t sep_fused3_init_device() {
     if ((e = set_attr_f3<1, 1>()) != cudaSuccess) return e;
     if ((e = set_attr_f3<1, 2>()) != cudaSuccess) return e;
     if ((e = set_attr_f3<3, 1>()) != cudaSuccess) return e;
+    if ((e = set_attr_f3<2, 1>()) != cudaSuccess) return e;
+    if ((e = set_attr_f3<2, 2>()) != cudaSuccess) return e;
     return set_attr_f3<3, 2>();
 }
 
@@ -743,6 +765,11 @@ cudaError_t launch_sep_fused3(const PwGemmPlan& p, const float* X, const float* 
     if (p.nsplit == 1) {
         if (stride == 1) BD_F3(1, 1);
         BD_F3(1, 2);
+    }
+    if (p.nsplit == 2) {
+        if (pair) return cudaErrorInvalidValue;           // the fp16 + fp8 plan is a one-CTA kernel
+        if (stride == 1) BD_F3(2, 1);
+        BD_F3(2, 2);
     }
     if (stride == 1) BD_F3(3, 1);
     BD_F3(3, 2);

@@ -54,6 +54,9 @@ extern "C" {
 #define BD_FUSE_PAIR (1 << 20)        /* fuse_mask bit: sep_fused3 issues cta_group::2 MMAs from CTA pairs (N >= 256 layers) */
 #define BD_FUSE_NO_TC_RESAMPLE (1 << 21) /* fuse_mask bit: resample tap by tap on CUDA cores instead of the tcgen05 GEMM */
 #define BD_PRECISION_FP16X3 3      /* tcgen05, hi/lo fp16 split, 3 MMAs: float32-equivalent (default)    */
+#define BD_PRECISION_FP16F8 2      /* tcgen05, A_hi W_hi in fp16 + both correction products as ONE e5m2 (FP8)
+                                      contraction: 2 MMA-equivalents, ~5e-5 on the logits (layers with K % 64 == 0
+                                      in the fused / GEMM kernels; the other layers keep the x3 split)          */
 
 typedef struct bd_engine bd_engine;
 
