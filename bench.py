@@ -594,7 +594,7 @@ def run_ours(args, rank, world, local):
     prof = eng.profile_device_ptr(d_x.data_ptr(), n, HOP_FRAMES)
     peaks = measured_peaks()
     from buzzdetect_b200.weights import LAYERS
-    mma_factor = {"fp16x3": 3, "fp16": 1, "fp32": 0}[args.precision]
+    mma_factor = {"fp16x3": 3, "fp16f8": 2, "fp16": 1, "fp32": 0}[args.precision]
     per_layer = {}
     def _f():
         return {"ms": 0.0, "launches": 0, "flop": 0.0, "bytes": 0.0}
@@ -732,7 +732,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("BUZZ_B200_PRECISION", "fp16x3"),
-                    choices=["fp16x3", "fp16", "fp32"])
+                    choices=["fp16x3", "fp16f8", "fp16", "fp32"])
     ap.add_argument("--hours", type=float, default=1.0, help="audio hours per step per GPU")
     ap.add_argument("--chunk-s", dest="chunk_s", type=float, default=199.68,
                     help="chunk length of the plugin end-to-end legs (reference default: 199.68 s)")

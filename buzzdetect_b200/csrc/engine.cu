@@ -1402,6 +1402,20 @@ int32_t bd_debug_pw_gemm(bd_engine* e, const float* A, const float* W, const flo
         BD_CHECK(e, pw_gemm_init_device());
         std::vector<__half> hi, lo;
         split_f16(A, na, hi, lo);
+        if (precision == BD_PRECISION_FP16F8) {
+            // second plane of A for the fp16 + fp8 plan: e5m2 bytes [M, 2K], per 64-channel k-block [lo * 2^11 | hi]
+            if (K % 64 != 0) return fail(e, "fp16f8 needs K % 64 == 0");
+            unsigned char* c8 = reinterpret_cast<unsigned char*>(lo.data());
+            std::vector<unsigned char> tmp(na * 2);
+            for (int64_t r = 0; r < M; ++r)
+                for (int64_t k = 0; k < K; ++k) {
+                    const float h = __half2float(hi[r * K + k]);
+                    unsigned char* row = tmp.data() + r * 2 * K + (k / 64) * 128 + (k % 64);
+                    row[0] = static_cast<unsigned char>(__nv_cvt_float_to_fp8((A[r * K + k] - h) * 2048.f, __NV_SATFINITE, __NV_E5M2));
+                    row[64] = static_cast<unsigned char>(__nv_cvt_float_to_fp8(h, __NV_SATFINITE, __NV_E5M2));
+                }
+            std::memcpy(c8, tmp.data(), na * 2);
+        }
         BD_CHECK(e, cudaMalloc(&a_hi, na * sizeof(__half)));
         BD_CHECK(e, cudaMalloc(&a_lo, na * sizeof(__half)));
         BD_CHECK(e, cudaMemcpyAsync(a_hi, hi.data(), na * sizeof(__half), cudaMemcpyHostToDevice, e->s_compute));
@@ -1409,7 +1423,9 @@ int32_t bd_debug_pw_gemm(bd_engine* e, const float* A, const float* W, const flo
         BD_CHECK(e, cudaMemcpyAsync(a_lo, lo.data(), na * sizeof(__half), cudaMemcpyHostToDevice, e->s_compute));
         BD_CHECK(e, cudaStreamSynchronize(e->s_compute));
         hi.resize(nw); lo.resize(nw);
-        const float out_scale = split_weights_f16(W, nw, hi.data(), lo.data());
+        const float out_scale = precision == BD_PRECISION_FP16F8
+            ? split_weights_f16f8(W, N, K, hi.data(), reinterpret_cast<unsigned char*>(lo.data()))
+            : split_weights_f16(W, nw, hi.data(), lo.data());
         BD_CHECK(e, cudaMalloc(&w_hi, nw * sizeof(__half)));
         BD_CHECK(e, cudaMalloc(&w_lo, nw * sizeof(__half)));
         BD_CHECK(e, cudaMemcpyAsync(w_hi, hi.data(), nw * sizeof(__half), cudaMemcpyHostToDevice, e->s_compute));
@@ -1418,7 +1434,8 @@ int32_t bd_debug_pw_gemm(bd_engine* e, const float* A, const float* W, const flo
         BD_CHECK(e, cudaStreamSynchronize(e->s_compute));
         PwGemmPlan plan;
         const char* perr = nullptr;
-        cudaError_t pe = pw_gemm_make_plan(&plan, a_hi, a_lo, M, K, w_hi, w_lo, N, precision == BD_PRECISION_FP16X3 ? 3 : 1,
+        cudaError_t pe = pw_gemm_make_plan(&plan, a_hi, a_lo, M, K, w_hi, w_lo, N,
+                                           precision == BD_PRECISION_FP16X3 ? 3 : (precision == BD_PRECISION_FP16F8 ? 2 : 1),
                                            block_n, out_scale, &perr);
         if (pe != cudaSuccess) rc = fail(e, std::string("plan: ") + (perr ? perr : cudaGetErrorString(pe)));
         if (rc == 0) {

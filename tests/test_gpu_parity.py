@@ -67,9 +67,11 @@ PW_SHAPES = [(1536 * 2, 64, 32), (384 * 3, 128, 64), (384, 128, 128), (96 * 5, 2
              (128 * 150, 128, 128)]
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16x3", "fp16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3", "fp16", "fp16f8"])
 @pytest.mark.parametrize("M,N,K", PW_SHAPES)
 def test_pw_gemm_matches_float64(engines, precision, M, N, K):
+    if precision == "fp16f8" and K % 64:
+        pytest.skip("the fp16 + fp8 plan works on 64-channel k-blocks")
     e = engines("fp32")
     rng = np.random.default_rng(M * 7 + N * 3 + K)
     A = np.maximum(rng.standard_normal((M, K)), 0).astype(np.float32) * 2.0
@@ -81,7 +83,7 @@ def test_pw_gemm_matches_float64(engines, precision, M, N, K):
         got = e.debug_pw_gemm(A, Wt, b, precision, bn)
         err = float(np.abs(got - ref).max()) / scale
         _report(f"pw_{precision}_M{M}_N{N}_K{K}_bn{bn}", err)
-        tol = {"fp32": 2e-6, "fp16x3": 4e-6, "fp16": 3e-3}[precision]
+        tol = {"fp32": 2e-6, "fp16x3": 4e-6, "fp16": 3e-3, "fp16f8": 2e-4}[precision]
         assert err <= tol, (precision, M, N, K, bn, err)
 
 
@@ -89,7 +91,8 @@ def test_pw_gemm_matches_float64(engines, precision, M, N, K):
 @pytest.mark.parametrize("precision,fuse_mask", [("fp32", 0), ("fp16x3", 0), ("fp16", 0), ("fp16x3", 0x7FF),
                                                  ("fp16", 0x7FF), ("fp16x3", 0x10002), ("fp32", 0x10000),
                                                  ("fp16x3", 0x20002), ("fp16", 0x20000), ("fp16x3", 0x507FF),
-                                                 ("fp16", 0x4003E), ("fp16x3", 0xC0006), ("fp16", 0x80000)])
+                                                 ("fp16", 0x4003E), ("fp16x3", 0xC0006), ("fp16", 0x80000),
+                                                 ("fp16f8", 0), ("fp16f8", 0x507FF), ("fp16f8", 0x1D07DE)])
 def test_every_stage_matches_oracle(engines, yamnet_variables, mel, precision, fuse_mask):
     """fuse_mask 0: separate depthwise / pointwise kernels (every intermediate is observable);
     0x7FF: layers 2..12 run as ONE fused kernel each (depthwise outputs stay in shared memory)."""
@@ -118,7 +121,7 @@ def test_every_stage_matches_oracle(engines, yamnet_variables, mel, precision, f
         err = float(np.abs(got - ref.ravel()).max()) / max(float(np.abs(ref).max()), 1e-6)
         worst[stage] = err
     _report(f"stages_{precision}_fuse{fuse_mask:x}", worst)
-    tol = 3e-2 if precision == "fp16" else 1e-4
+    tol = {"fp16": 3e-2, "fp16f8": 1e-3}.get(precision, 1e-4)
     bad = {s: v for s, v in worst.items() if not v <= tol}
     assert not bad, bad
 
@@ -134,7 +137,8 @@ def _median_threshold(a):
     ("fp16x3", 48, 33.1, 0x10002), ("fp16", 96, 20.0, 0x20000), ("fp16x3", 96, 61.3, 0x5003E),
     ("fp16x3", 48, 33.1, 0x507FF), ("fp16x3", 96, 61.3, 0xC0006), ("fp16x3", 48, 33.1, 0xC0006),
     ("fp16x3", 96, 61.3, 0x10002), ("fp16x3", 96, 61.3, 0x1D07DE), ("fp16x3", 48, 33.1, 0x1D07FE),
-    ("fp16", 96, 20.0, 0x1D07DE),
+    ("fp16", 96, 20.0, 0x1D07DE), ("fp16f8", 96, 61.3, -1), ("fp16f8", 48, 33.1, -1), ("fp16f8", 96, 61.3, 0),
+    ("fp16f8", 96, 199.68, -1),
 ])
 def test_predict_matches_oracle(engines, yamnet_variables, mel, head, precision, hop, seconds, fuse_mask):
     e = engines(precision, early_patches=16, late_patches=48, fuse_mask=fuse_mask)   # several early / late sub-batches
@@ -155,8 +159,8 @@ def test_predict_matches_oracle(engines, yamnet_variables, mel, head, precision,
     if precision == "fp16":
         assert a_err <= 5e-3 * float(np.abs(want).max())
     else:
-        assert a_err <= 1e-3, a_err
-        assert e_err <= 1e-4, e_err
+        assert a_err <= (2e-4 if precision == "fp16f8" else 1e-3), a_err      # fp16f8: the adoption bar of VERDICT r1 item 7
+        assert e_err <= (4e-4 if precision == "fp16f8" else 1e-4), e_err
         assert flips == 0
 
 
