@@ -736,7 +736,7 @@ cudaError_t launch_sep_fused3(const PwGemmPlan& p, const float* X, const float* 
     // audio-hour, layer 6: 0.305 vs 0.213): the pair couples two stencil / epilogue pipelines behind one issuer and the
     // peer's half of B does not arrive faster than a second local copy would.  Opt-in (BD_FUSE_PAIR / BD_F3_PAIR=1).
     static const int pair_env = [] { const char* e = getenv("BD_F3_PAIR"); return e ? atoi(e) : 0; }();
-    const bool pair = (cta_pairs || pair_env != 0) && num_sms >= 2 && nacc >= 256 && passes >= 2;
+    const bool pair = (cta_pairs || pair_env != 0) && num_sms >= 2 && nacc >= 256 && passes >= 2 && p.nsplit != 2;
     if (pair) {
         const long long pair_passes = (static_cast<long long>(prm.m_tiles) + 1) / 2 * (p.N / nacc);
         grid = static_cast<int>(2 * pair_passes < num_sms ? 2 * pair_passes : num_sms);
