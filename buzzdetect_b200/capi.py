@@ -64,6 +64,8 @@ SIGNATURES = {
                                        C.c_int32, C.c_void_p, C.c_void_p, _i64p]),
     "bd_wait": (C.c_int32, [C.c_void_p, C.c_int32]),
     "bd_flush": (C.c_int32, [C.c_void_p]),
+    "bd_reserve_slots": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32]),
+    "bd_debug_stats": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "bd_set_auto_flush": (C.c_int32, [C.c_void_p, C.c_int32]),
     "bd_slot_state": (C.c_int32, [C.c_void_p, C.c_int32]),
     "bd_batch_stats": (C.c_int32, [C.c_void_p, _i64p, _i64p]),
@@ -311,6 +313,8 @@ class Engine:
         _, _, P = frames_for(x.size, hop_frames)
         act = np.empty((P, self.n_classes), dtype=np.float32)
         emb = np.empty((P, EMBED_DIM), dtype=np.float32) if want_embeddings else None
+        if x.size > getattr(self, "_reserved", 0) and not self._outstanding:
+            self.reserve(x.size, getattr(self, "_reserved_pcm", 0), hop_frames)
         slot = self._acquire_slot(x.size)
         tk = self._register(slot, act, emb, x.size, x)
         try:
@@ -334,6 +338,8 @@ class Engine:
         n_out = int(self._lib.bd_resample_out_len(a.shape[0], src_rate))
         _, _, P = frames_for(n_out, hop_frames)
         act = np.empty((P, self.n_classes), dtype=np.float32)
+        if (n_out > getattr(self, "_reserved", 0) or a.nbytes > getattr(self, "_reserved_pcm", 0)) and not self._outstanding:
+            self.reserve(n_out, a.nbytes, hop_frames)
         slot = self._acquire_slot(n_out)
         tk = self._register(slot, act, None, n_out, a)
         try:
@@ -344,6 +350,17 @@ class Engine:
             raise
         assert got == P
         return tk
+
+    def reserve(self, n_samples: int, pcm_bytes: int = 0, hop_frames: int = 96):
+        """Pre-size every free slot for chunks of this size (no allocation while chunks are in flight)."""
+        self._check(self._lib.bd_reserve_slots(self._h, int(n_samples), int(pcm_bytes), int(hop_frames)), "bd_reserve_slots")
+        self._reserved = max(getattr(self, "_reserved", 0), int(n_samples))
+        self._reserved_pcm = max(getattr(self, "_reserved_pcm", 0), int(pcm_bytes))
+
+    def debug_stats(self) -> str:
+        buf = C.create_string_buffer(512)
+        self._check(self._lib.bd_debug_stats(self._h, buf, 512), "bd_debug_stats")
+        return buf.value.decode()
 
     def set_auto_flush(self, on: bool):
         """False: submitted chunks are only launched by flush() / a ticket's wait() (deterministic batches)."""

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <map>
 #include <chrono>
@@ -131,6 +132,9 @@ struct bd_engine {
     bool stop = false, flush_req = false;
     cudaEvent_t ev_pass[2] = {nullptr, nullptr};   // end of compute of pass i (i & 1)
     int64_t pass_seq = 0;
+    // diagnostics (bd_debug_stats)
+    int64_t st_sleep_full = 0, st_sleep_small = 0, st_sleep_noarr = 0, st_allocs = 0;
+    double st_launch_s = 0.0, st_submit_s = 0.0, st_alloc_s = 0.0;
     int64_t batches = 0, batched_chunks = 0;
     bool auto_flush = true;               // bd_set_auto_flush(0): chunks wait until bd_wait / bd_flush (tests, batch drivers)
     int64_t coalesce_target = 3072;       // pending patches that trigger a launch even while the GPU is busy
@@ -435,7 +439,15 @@ int run_chunk(bd_engine* e, const float* x, int64_t n, int hop_frames, float* d_
     return 0;
 }
 
+struct StopWatch {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    double s() const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 int ensure_slot(bd_engine* e, Slot& s, int64_t n, int64_t P) {
+    StopWatch sw;
+    struct Acc { bd_engine* e; StopWatch& sw; bool on = false; ~Acc() { if (on) { e->st_alloc_s += sw.s(); e->st_allocs++; } } } acc{e, sw};
+    if (n > s.in_cap || P > s.out_cap) acc.on = true;
     if (n > s.in_cap) {
         if (s.d_in) cudaFree(s.d_in);
         s.d_in = nullptr;
@@ -645,8 +657,13 @@ void dispatcher_main(bd_engine* e) {
         cudaGetLastError();
         const bool go = n_arr > 0 && (inflight == 0 || (inflight == 1 && arrived >= e->coalesce_target));
         if (go) {
+            StopWatch sw;
             launch_pending(e, true);
+            e->st_launch_s += sw.s();
         } else {
+            if (inflight == 2) e->st_sleep_full++;
+            else if (n_arr == 0) e->st_sleep_noarr++;
+            else e->st_sleep_small++;
             lk.unlock();
             std::this_thread::sleep_for(std::chrono::microseconds(15));
             lk.lock();
@@ -1052,6 +1069,44 @@ int32_t bd_wait(bd_engine* e, int32_t slot) {
     if (s.user_act) std::memcpy(s.user_act, s.h_act, static_cast<size_t>(s.P) * e->n_classes * sizeof(float));
     if (s.user_emb) std::memcpy(s.user_emb, s.h_emb, static_cast<size_t>(s.P) * kEmb * sizeof(float));
     s.user_act = s.user_emb = nullptr;
+    return 0;
+}
+
+int32_t bd_debug_stats(bd_engine* e, char* buf, size_t len) {
+    if (!e || !buf || !len) return 1;
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
+    snprintf(buf, len, "passes=%lld chunks=%lld launch_s=%.4f alloc_s=%.4f allocs=%lld polls{two_in_flight=%lld, waiting_for_running_pass=%lld, "
+                       "nothing_arrived=%lld}",
+             (long long)e->batches, (long long)e->batched_chunks, e->st_launch_s, e->st_alloc_s, (long long)e->st_allocs,
+             (long long)e->st_sleep_full, (long long)e->st_sleep_small, (long long)e->st_sleep_noarr);
+    return 0;
+}
+
+/* Pre-size every slot for chunks of up to n_samples 16 kHz samples / pcm_bytes of decoded PCM (0: none), so that no
+ * device or pinned allocation happens while chunks are in flight (cudaMalloc and cudaHostAlloc synchronise). */
+int32_t bd_reserve_slots(bd_engine* e, int64_t n_samples, int64_t pcm_bytes, int32_t hop_frames) {
+    if (!e) return 1;
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
+    if (n_samples < 0 || pcm_bytes < 0 || hop_frames < 1 || hop_frames > kPatchFrames) return fail(e, "bad arguments");
+    BD_CHECK(e, cudaSetDevice(e->device));
+    int64_t P = 0;
+    frames_for(n_samples, hop_frames, nullptr, nullptr, &P);
+    for (auto& s : e->slots) {
+        if (s.state != 0) continue;
+        if (ensure_slot(e, s, n_samples, P)) return 1;
+        if (ensure_staging(e, s, P * e->n_classes, 0)) return 1;
+        if (pcm_bytes > s.pcm_cap) {
+            if (s.d_pcm) cudaFree(s.d_pcm);
+            s.d_pcm = nullptr;
+            s.pcm_cap = 0;
+            const int64_t cap = ((pcm_bytes + 65535) / 65536) * 65536;
+            BD_CHECK(e, cudaMalloc(&s.d_pcm, cap));
+            s.pcm_cap = cap;
+        }
+    }
+    for (int set = 0; set < 2; ++set)
+        if (!e->d_act_batch[set])
+            BD_CHECK(e, cudaMalloc(&e->d_act_batch[set], static_cast<size_t>(e->S2) * e->n_classes * sizeof(float)));
     return 0;
 }
 

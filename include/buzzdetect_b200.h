@@ -119,6 +119,9 @@ int32_t bd_submit_pcm_host(bd_engine* e, int32_t slot, const void* pcm, int32_t 
 int32_t bd_wait(bd_engine* e, int32_t slot);
 int32_t bd_flush(bd_engine* e);                  /* launch every pending chunk now (does not wait)                      */
 int32_t bd_synchronize(bd_engine* e);
+int32_t bd_reserve_slots(bd_engine* e, int64_t n_samples, int64_t pcm_bytes, int32_t hop_frames);
+                                                 /* pre-size every slot (device + pinned buffers) for chunks of this size */
+int32_t bd_debug_stats(bd_engine* e, char* buf, size_t len);   /* dispatcher counters, human readable               */
 int32_t bd_set_auto_flush(bd_engine* e, int32_t on);   /* 0: submitted chunks wait for bd_wait / bd_flush (default 1) */
 int32_t bd_slot_state(bd_engine* e, int32_t slot);   /* 0 free, 1 pending, 2 launched; -1 bad argument                 */
 int32_t bd_batch_stats(bd_engine* e, int64_t* batches, int64_t* chunks);   /* CNN passes launched / chunks they carried */
