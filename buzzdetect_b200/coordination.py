@@ -506,9 +506,12 @@ def run_analysis(paths: list[str], dir_out: str, gpus: list[int] | None = None, 
     if model_factory is None:
         from .inference.models import load_model
 
+        factory_lock = threading.Lock()
+
         def model_factory(gpu):
-            os.environ["BUZZ_B200_DEVICE"] = str(gpu)
-            return load_model(modelname, framehop_prop=framehop_prop, initialize=True)
+            with factory_lock:                      # the plugin reads its device from the environment at initialize()
+                os.environ["BUZZ_B200_DEVICE"] = str(gpu)
+                return load_model(modelname, framehop_prop=framehop_prop, initialize=True)
         if alloc is None:
             from . import capi
             alloc = capi.pinned_empty
