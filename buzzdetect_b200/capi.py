@@ -66,6 +66,7 @@ SIGNATURES = {
     "bd_flush": (C.c_int32, [C.c_void_p]),
     "bd_reserve_slots": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32]),
     "bd_debug_stats": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_size_t]),
+    "bd_trace": (C.c_int32, [C.c_void_p, C.c_int32, C.c_char_p, C.c_size_t]),
     "bd_set_auto_flush": (C.c_int32, [C.c_void_p, C.c_int32]),
     "bd_slot_state": (C.c_int32, [C.c_void_p, C.c_int32]),
     "bd_batch_stats": (C.c_int32, [C.c_void_p, _i64p, _i64p]),
@@ -361,6 +362,19 @@ class Engine:
         buf = C.create_string_buffer(512)
         self._check(self._lib.bd_debug_stats(self._h, buf, 512), "bd_debug_stats")
         return buf.value.decode()
+
+    def trace(self, on: bool):
+        """True: start the slot-API timeline.  False: stop; returns [(kind, a, b, host_ms, device_ms), ...]."""
+        if on:
+            self._check(self._lib.bd_trace(self._h, 1, None, 0), "bd_trace")
+            return None
+        buf = C.create_string_buffer(1 << 20)
+        self._check(self._lib.bd_trace(self._h, 0, buf, len(buf)), "bd_trace")
+        out = []
+        for line in buf.value.decode().splitlines():
+            k, a, b, h, d = line.split()
+            out.append((int(k), int(a), int(b), float(h), float(d)))
+        return out
 
     def set_auto_flush(self, on: bool):
         """False: submitted chunks are only launched by flush() / a ticket's wait() (deterministic batches)."""

@@ -143,6 +143,12 @@ struct bd_engine {
     std::map<GraphKey, cudaGraphExec_t> graphs;
     std::map<GraphKey, int64_t> graph_launches;
     int64_t launch_count = 0;
+    // timeline trace (bd_trace): host clock + timing events at every hand-over of the slot API
+    struct TraceRec { int kind, a, b; double host_ms; cudaEvent_t ev; };
+    bool tracing = false;
+    std::vector<TraceRec> trace;
+    cudaEvent_t trace_base = nullptr;
+    std::chrono::steady_clock::time_point trace_t0;
     // profiling hooks (bd_profile_device)
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;
@@ -216,6 +222,20 @@ void mark(bd_engine* e, int cat, cudaStream_t st) {
     cudaEventRecord(ev, st);
     e->prof_events.push_back(ev);
     e->prof_cat.push_back(cat);
+}
+
+// Timeline trace: kinds 0 submit call (a = slot), 1 input copy done (a = slot), 2 pass begins on the device
+// (a = pass, b = chunks), 3 pass ends, 4 result copy done (a = slot), 5 bd_wait returns (a = slot), 6 host side of the
+// pass launch finished (a = pass).  st == nullptr: host time only.
+void trace_point(bd_engine* e, int kind, int a, int b, cudaStream_t st) {
+    if (!e->tracing) return;
+    bd_engine::TraceRec r{kind, a, b, 0.0, nullptr};
+    r.host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - e->trace_t0).count();
+    if (st) {
+        cudaEventCreate(&r.ev);
+        cudaEventRecord(r.ev, st);
+    }
+    e->trace.push_back(r);
 }
 
 // ------------------------------------------------------------------------------------------ the pipeline
@@ -526,16 +546,21 @@ int launch_group(bd_engine* e, const std::vector<int>& group, const std::vector<
             if (run_resample(e, r, s.d_pcm, s.pcm_fmt, s.pcm_channels, s.pcm_frames, s.d_in, s.n, e->s_compute)) return 1;
         }
     }
+    const int pass_id = static_cast<int>(e->pass_seq - 1);
+    trace_point(e, 2, pass_id, static_cast<int>(group.size()), e->s_compute);
     if (group.size() == 1) {
         Slot& s = e->slots[group[0]];
         if (run_chunk(e, s.d_in, s.n, hop, s.d_act, s.want_emb ? s.d_emb : nullptr, s.P, s.P >= 512)) return 1;
         BD_CHECK(e, cudaEventRecord(s.ev_comp, e->s_compute));
         BD_CHECK(e, cudaEventRecord(ev_pass, e->s_compute));
+        trace_point(e, 3, pass_id, 1, e->s_compute);
         BD_CHECK(e, cudaStreamWaitEvent(e->s_out, s.ev_comp, 0));
         BD_CHECK(e, cudaMemcpyAsync(outs[0].act, s.d_act, s.P * e->n_classes * sizeof(float), cudaMemcpyDeviceToHost, e->s_out));
         if (s.want_emb)
             BD_CHECK(e, cudaMemcpyAsync(outs[0].emb, s.d_emb, s.P * kEmb * sizeof(float), cudaMemcpyDeviceToHost, e->s_out));
         BD_CHECK(e, cudaEventRecord(s.ev_out, e->s_out));
+        trace_point(e, 4, group[0], 0, e->s_out);
+        trace_point(e, 6, pass_id, 0, nullptr);
         e->batches++; e->batched_chunks++;
         return 0;
     }
@@ -570,6 +595,7 @@ int launch_group(bd_engine* e, const std::vector<int>& group, const std::vector<
     Slot& s0 = e->slots[group[0]];
     BD_CHECK(e, cudaEventRecord(s0.ev_comp, e->s_compute));
     BD_CHECK(e, cudaEventRecord(ev_pass, e->s_compute));
+    trace_point(e, 3, pass_id, static_cast<int>(group.size()), e->s_compute);
     BD_CHECK(e, cudaStreamWaitEvent(e->s_out, s0.ev_comp, 0));
     for (size_t i = 0; i < group.size(); ++i) {
         Slot& s = e->slots[group[i]];
@@ -579,7 +605,9 @@ int launch_group(bd_engine* e, const std::vector<int>& group, const std::vector<
             BD_CHECK(e, cudaMemcpyAsync(outs[i].emb, e->d_emb_batch[set] + g0[i] * kEmb, s.P * kEmb * sizeof(float),
                                         cudaMemcpyDeviceToHost, e->s_out));
         BD_CHECK(e, cudaEventRecord(s.ev_out, e->s_out));
+        trace_point(e, 4, group[i], 0, e->s_out);
     }
+    trace_point(e, 6, pass_id, 0, nullptr);
     BD_CHECK(e, cudaEventRecord(e->ev_batch_out[set], e->s_out));
     e->batches++; e->batched_chunks += static_cast<int64_t>(group.size());
     return 0;
@@ -1037,8 +1065,10 @@ int32_t bd_submit_host(bd_engine* e, int32_t slot, const float* samples, int64_t
     if (ensure_slot(e, s, n, P)) return 1;
     s.n = n; s.P = P; s.hop = hop_frames; s.want_emb = emb != nullptr; s.has_pcm = false; s.arrived = false;
     if (route_outputs(e, s, act, emb)) return 1;
+    trace_point(e, 0, slot, 0, nullptr);
     BD_CHECK(e, cudaMemcpyAsync(s.d_in, samples, n * sizeof(float), cudaMemcpyHostToDevice, e->s_in));
     BD_CHECK(e, cudaEventRecord(s.ev_in, e->s_in));
+    trace_point(e, 1, slot, 0, e->s_in);
     s.state = 1;
     e->pending.push_back(slot);
     return maybe_flush(e);
@@ -1069,6 +1099,42 @@ int32_t bd_wait(bd_engine* e, int32_t slot) {
     if (s.user_act) std::memcpy(s.user_act, s.h_act, static_cast<size_t>(s.P) * e->n_classes * sizeof(float));
     if (s.user_emb) std::memcpy(s.user_emb, s.h_emb, static_cast<size_t>(s.P) * kEmb * sizeof(float));
     s.user_act = s.user_emb = nullptr;
+    trace_point(e, 5, slot, 0, nullptr);
+    return 0;
+}
+
+/* on = 1: start recording (drains the streams first).  on = 0: stop, drain, and write one line per record
+ * "kind a b host_ms device_ms" (device_ms = -1 for host-only records; both clocks start at the bd_trace(1) call). */
+int32_t bd_trace(bd_engine* e, int32_t on, char* buf, size_t len) {
+    if (!e) return 1;
+    if (bd_synchronize(e)) return 1;
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
+    BD_CHECK(e, cudaSetDevice(e->device));
+    if (on) {
+        for (auto& r : e->trace) if (r.ev) cudaEventDestroy(r.ev);
+        e->trace.clear();
+        if (!e->trace_base) BD_CHECK(e, cudaEventCreate(&e->trace_base));
+        BD_CHECK(e, cudaEventRecord(e->trace_base, e->s_compute));
+        BD_CHECK(e, cudaEventSynchronize(e->trace_base));
+        e->trace_t0 = std::chrono::steady_clock::now();
+        e->tracing = true;
+        return 0;
+    }
+    e->tracing = false;
+    size_t pos = 0;
+    if (buf && len) buf[0] = 0;
+    for (auto& r : e->trace) {
+        float ms = -1.f;
+        if (r.ev) {
+            cudaEventSynchronize(r.ev);
+            cudaEventElapsedTime(&ms, e->trace_base, r.ev);
+            cudaEventDestroy(r.ev);
+            r.ev = nullptr;
+        }
+        if (buf && pos + 64 < len)
+            pos += static_cast<size_t>(snprintf(buf + pos, len - pos, "%d %d %d %.4f %.4f\n", r.kind, r.a, r.b, r.host_ms, ms));
+    }
+    e->trace.clear();
     return 0;
 }
 
@@ -1372,8 +1438,10 @@ int32_t bd_submit_pcm_host(bd_engine* e, int32_t slot, const void* pcm, int32_t 
     if (src_rate != 16000 && get_resampler(e, src_rate, &r)) return 1;
     s.n = n; s.P = P; s.hop = hop_frames; s.want_emb = emb != nullptr; s.arrived = false;
     if (route_outputs(e, s, act, emb)) return 1;
+    trace_point(e, 0, slot, 0, nullptr);
     if (n_frames > 0) BD_CHECK(e, cudaMemcpyAsync(s.d_pcm, pcm, pcm_bytes, cudaMemcpyHostToDevice, e->s_in));
     BD_CHECK(e, cudaEventRecord(s.ev_in, e->s_in));
+    trace_point(e, 1, slot, 0, e->s_in);
     // downmix + resample to the slot's 16 kHz buffer run at the head of the pass that takes the chunk (launch_group)
     s.has_pcm = true; s.pcm_fmt = fmt; s.pcm_channels = channels; s.pcm_rate = src_rate; s.pcm_frames = n_frames;
     s.state = 1;

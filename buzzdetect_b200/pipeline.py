@@ -317,8 +317,10 @@ def analyze_wav(path_audio: str, dir_out: str, engine: "capi.Engine", classes: l
                 digits_results: int = 2, n_in_flight: int = 8, only_chunks=None, readers: int = 2, log=None,
                 stop_event: threading.Event | None = None) -> dict:
     """One audio file (any format) through the path.  Resumes from `<ident>_buzzpart.csv` if present; skips finished
-    files.  only_chunks: indices into the file's chunk list that THIS rank processes (chunk-range sharding of one long
-    file over several GPUs); the file is finalised by whichever rank finds it covered.  Returns a small report."""
+    files.  only_chunks: the (start, end) chunks of the file that THIS rank processes (chunk-range sharding of one long
+    file over several GPUs, taken from make_plan(...).chunks -- the chunks themselves, not indices: the chunk list
+    re-derived here shrinks as other ranks append their rows); the file is finalised by whichever rank finds it covered.
+    Returns a small report."""
     log = log or _default_log
     ident = os.path.splitext(os.path.basename(path_audio))[0]
     partial = os.path.join(dir_out, ident + cfg.SUFFIX_RESULT_PARTIAL)
@@ -347,7 +349,9 @@ def analyze_wav(path_audio: str, dir_out: str, engine: "capi.Engine", classes: l
         _finalise(partial, complete)
         track.close()
         return report
-    mine = list(range(len(chunklist))) if only_chunks is None else sorted(i for i in only_chunks if 0 <= i < len(chunklist))
+    if only_chunks is not None:
+        chunklist = sorted((float(a), float(b)) for a, b in only_chunks)
+    mine = list(range(len(chunklist)))
     sr, ch = track.samplerate, track.channels
     n_ring = max(2, min(int(n_in_flight), engine.n_slots))
     positioned = isinstance(track, WavTrack)     # pread: reader threads work ahead; a decoder is a sequential stream
@@ -458,8 +462,14 @@ def make_plan(paths: list[str], dir_out: str, world_size: int, chunklength: floa
             lists.append(stream.file_chunklist(t.duration, chunklength, covered))
         finally:
             t.close()
-    plan = shard.plan(lists, world_size)
-    return [[(w.file_index, w.chunk_index) for w in r] for r in plan]
+    plan = _Plan([(w.file_index, w.chunk_index) for w in r] for r in shard.plan(lists, world_size))
+    plan.chunks = {(fi, ci): c for fi, l in enumerate(lists) for ci, c in enumerate(l)}
+    return plan
+
+
+class _Plan(list):
+    """[rank] -> [(file index, chunk index)]; .chunks maps (file index, chunk index) -> (start, end) seconds."""
+    chunks: dict
 
 
 def analyze_files(paths: list[str], dir_out: str, rank: int = 0, world_size: int = 1, device: int | None = None,
@@ -479,5 +489,5 @@ def analyze_files(paths: list[str], dir_out: str, rank: int = 0, world_size: int
     out = []
     for fi in sorted(work):
         out.append(analyze_wav(paths[fi], dir_out, model.model, model.config["classes"],
-                               only_chunks=None if fi in whole else work[fi], **kw))
+                               only_chunks=None if fi in whole else [plan.chunks[(fi, ci)] for ci in work[fi]], **kw))
     return out

@@ -122,6 +122,8 @@ int32_t bd_synchronize(bd_engine* e);
 int32_t bd_reserve_slots(bd_engine* e, int64_t n_samples, int64_t pcm_bytes, int32_t hop_frames);
                                                  /* pre-size every slot (device + pinned buffers) for chunks of this size */
 int32_t bd_debug_stats(bd_engine* e, char* buf, size_t len);   /* dispatcher counters, human readable               */
+int32_t bd_trace(bd_engine* e, int32_t on, char* buf, size_t len);   /* timeline of the slot API: 1 start, 0 stop + dump
+                                                 ("kind a b host_ms device_ms" per line; kinds in csrc/engine.cu)      */
 int32_t bd_set_auto_flush(bd_engine* e, int32_t on);   /* 0: submitted chunks wait for bd_wait / bd_flush (default 1) */
 int32_t bd_slot_state(bd_engine* e, int32_t slot);   /* 0 free, 1 pending, 2 launched; -1 bad argument                 */
 int32_t bd_batch_stats(bd_engine* e, int64_t* batches, int64_t* chunks);   /* CNN passes launched / chunks they carried */

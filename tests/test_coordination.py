@@ -305,7 +305,7 @@ def test_bad_read_and_chunk_range_sharding_on_gpu(tmp_path, engines):
     plan = pipeline.make_plan([wav], out_b, world_size=3, chunklength=9.6)
     assert [len(p) for p in plan] == [2, 2, 2]
     for rank in (2, 0, 1):
-        rr = pipeline.analyze_wav(wav, out_b, e, CLASSES, chunklength=9.6, only_chunks=[ci for _, ci in plan[rank]])
+        rr = pipeline.analyze_wav(wav, out_b, e, CLASSES, chunklength=9.6, only_chunks=[plan.chunks[w] for w in plan[rank]])
         assert rr["chunks"] == 2
         assert os.path.exists(os.path.join(out_b, "rec_buzzdetect.csv")) == (rank == 1)     # the last rank finalises
     assert open(os.path.join(out_b, "rec_buzzdetect.csv")).read() == full
