@@ -36,11 +36,12 @@ cudaError_t launch_logmel(const float* x, long long n_valid, long long frame_beg
 // ---- frontend2.cu  (version 2: 16 x 16 FFT across half-warps, lane = frame mel, TMA in/out, segment table)
 constexpr int kMaxLogmelSegs = 64;
 struct LogmelSeg {                 // one independent chunk of 16 kHz audio inside a batched launch
-    const float* x;                // device samples
+    const float* x;                // device samples (fmt 0: float32; fmt 1: int16 PCM, value = s / 32768 as soundfile reads it)
     long long n_valid;             // samples that exist (reads beyond are the virtual zero padding of pad_waveform)
     long long frame_begin;         // first STFT frame to compute (frame f covers samples 160 f .. 160 f + 399)
     int row_begin;                 // first row of the shared log-mel buffer this segment writes
     int n_rows;                    // number of frames
+    int fmt = 0;                   // 0 float32, 1 int16 (16 kHz mono PCM straight from the decoder: no conversion pass)
 };
 struct alignas(16) FrontendMelParam { unsigned char raw[4912]; };   // opaque image of the kernel's mel parameter block
 cudaError_t frontend2_init_device();

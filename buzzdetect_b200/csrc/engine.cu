@@ -536,10 +536,15 @@ int launch_group(bd_engine* e, const std::vector<int>& group, const std::vector<
     const int hop = e->slots[group[0]].hop;
     cudaEvent_t ev_pass = e->ev_pass[e->pass_seq & 1];
     e->pass_seq++;
+    // 16 kHz mono int16 PCM needs no resampler: the frontend reads it as it lies in the slot (LogmelSeg::fmt = 1), which
+    // saves a conversion kernel per chunk and 6 bytes of HBM traffic per sample
+    auto direct16 = [&](const Slot& s) {
+        return s.has_pcm && s.pcm_fmt == 1 && s.pcm_channels == 1 && s.pcm_rate == 16000 && !e->frontend_v1 && s.P <= e->S2;
+    };
     for (int si : group) {
         Slot& s = e->slots[si];
         BD_CHECK(e, cudaStreamWaitEvent(e->s_compute, s.ev_in, 0));
-        if (s.has_pcm) {
+        if (s.has_pcm && !direct16(s)) {
             bd_engine::Resampler ident{1, 1, 1, nullptr};
             bd_engine::Resampler* r = &ident;
             if (s.pcm_rate != 16000 && get_resampler(e, s.pcm_rate, &r)) return 1;
@@ -548,7 +553,7 @@ int launch_group(bd_engine* e, const std::vector<int>& group, const std::vector<
     }
     const int pass_id = static_cast<int>(e->pass_seq - 1);
     trace_point(e, 2, pass_id, static_cast<int>(group.size()), e->s_compute);
-    if (group.size() == 1) {
+    if (group.size() == 1 && !direct16(e->slots[group[0]])) {
         Slot& s = e->slots[group[0]];
         if (run_chunk(e, s.d_in, s.n, hop, s.d_act, s.want_emb ? s.d_emb : nullptr, s.P, s.P >= 512)) return 1;
         BD_CHECK(e, cudaEventRecord(s.ev_comp, e->s_compute));
@@ -574,7 +579,8 @@ int launch_group(bd_engine* e, const std::vector<int>& group, const std::vector<
         const bool last = i + 1 == group.size();
         g0[i] = g;
         LogmelSeg& sg = job.segs[job.n_segs++];
-        sg.x = s.d_in;
+        sg.fmt = direct16(s) ? 1 : 0;
+        sg.x = sg.fmt ? reinterpret_cast<const float*>(s.d_pcm) : s.d_in;
         sg.n_valid = s.n;
         sg.frame_begin = 0;
         sg.row_begin = static_cast<int>(g * hop);

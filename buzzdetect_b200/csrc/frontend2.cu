@@ -68,7 +68,7 @@ struct FeSeg {
     int row_begin;                 // first log-mel row written
     int n_rows;                    // frames to compute
     int tile_begin;                // prefix sum of tiles
-    int pad_;
+    int fmt;                       // 0 float32 samples, 1 int16 PCM
 };
 
 struct FeSegs {
@@ -170,6 +170,11 @@ __device__ __forceinline__ float2 lds64(uint32_t a) {
 __device__ __forceinline__ void sts64f(uint32_t a, float2 v) {
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
 }
+__device__ __forceinline__ uint32_t lds32u(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
 __device__ __forceinline__ float lds32(uint32_t a) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
@@ -186,6 +191,7 @@ struct TileInfo {
     int row0;              // first log-mel row of the tile
     int rows_valid;        // 32, or n_rows of a segment shorter than one tile
     bool tma;
+    bool pcm16;            // the tile holds int16 PCM: the FFT runs on the integer values, the mel sums are scaled by 2^-15
 };
 
 __global__ void __launch_bounds__(kFeThreads, 2)
@@ -246,6 +252,7 @@ logmel2_kernel(const __grid_constant__ FeSegs segs, const __grid_constant__ FeMe
         ti.g0 = (sg.frame_begin + f0) * static_cast<long long>(kHop);
         ti.row0 = sg.row_begin + f0;
         ti.tma = (reinterpret_cast<uintptr_t>(sg.x) & 15u) == 0 && ti.g0 + kTileSamples <= sg.n_valid;
+        ti.pcm16 = sg.fmt == 1;
         return ti;
     };
     // the tile's 5360 samples -> shared memory: one TMA bulk copy when the tile lies inside the segment (and the base is
@@ -254,8 +261,18 @@ logmel2_kernel(const __grid_constant__ FeSegs segs, const __grid_constant__ FeMe
         if (ti.tma) {
             if (tid == 0) {
                 fence_proxy_async_smem();                           // earlier generic-proxy accesses to the buffer are ordered
-                mbar_arrive_expect_tx(bar, kTileSamples * 4);
-                bulk_load_1d(smem_u32(samp), ti.x + ti.g0, kTileSamples * 4, bar);
+                const uint32_t bytes = ti.pcm16 ? kTileSamples * 2 : kTileSamples * 4;
+                const void* src = ti.pcm16 ? static_cast<const void*>(reinterpret_cast<const short*>(ti.x) + ti.g0)
+                                           : static_cast<const void*>(ti.x + ti.g0);
+                mbar_arrive_expect_tx(bar, bytes);
+                bulk_load_1d(smem_u32(samp), src, bytes, bar);
+            }
+        } else if (ti.pcm16) {
+            const short* xs16 = reinterpret_cast<const short*>(ti.x);
+            short* s16 = reinterpret_cast<short*>(samp);
+            for (int i = tid; i < kTileSamples; i += kFeThreads) {
+                const long long g = ti.g0 + i;
+                s16[i] = g < ti.n_valid ? __ldg(xs16 + g) : static_cast<short>(0);
             }
         } else {
             for (int i = tid; i < kTileSamples; i += kFeThreads) {
@@ -286,14 +303,26 @@ logmel2_kernel(const __grid_constant__ FeSegs segs, const __grid_constant__ FeMe
             // this half-warp's frame within the tile; the two halves are 4 frames apart so that their magnitude rows
             // (260 floats each) fall into disjoint bank halves
             const int f = (warp & 3) + 4 * h + 8 * (warp >> 2) + 16 * r;
-            const uint32_t xs = samp_u32 + static_cast<uint32_t>((f * kHop + 2 * l) * 4);
             float2 v[16];
+            if (cur.pcm16) {
+                // int16 PCM: the transform is linear and a power-of-two scale commutes with every rounding in it, so the
+                // FFT runs on the integer sample values and the 2^-15 of soundfile's float32 conversion is applied to the
+                // mel sums -- bit-identical to converting first, without the conversion pass or its 6 bytes per sample
+                const uint32_t xs = samp_u32 + static_cast<uint32_t>((f * kHop + 2 * l) * 2);
 #pragma unroll
-            for (int n1 = 0; n1 < 12; ++n1) {
-                const float2 sv = lds64(xs + 32 * 4 * n1);
-                v[n1] = make_float2(sv.x * wreg[n1].x, sv.y * wreg[n1].y);
-            }
-            {
+                for (int n1 = 0; n1 < 13; ++n1) {
+                    const uint32_t u = lds32u(n1 < 12 || l < 8 ? xs + 32 * 2 * n1 : xs);
+                    const float s0 = static_cast<float>(static_cast<short>(u & 0xFFFFu));
+                    const float s1 = static_cast<float>(static_cast<int>(u) >> 16);
+                    v[n1] = make_float2(s0 * wreg[n1].x, s1 * wreg[n1].y);
+                }
+            } else {
+                const uint32_t xs = samp_u32 + static_cast<uint32_t>((f * kHop + 2 * l) * 4);
+#pragma unroll
+                for (int n1 = 0; n1 < 12; ++n1) {
+                    const float2 sv = lds64(xs + 32 * 4 * n1);
+                    v[n1] = make_float2(sv.x * wreg[n1].x, sv.y * wreg[n1].y);
+                }
                 // samples 384..399 (lanes l < 8); beyond them the 512-point frame is zero padding.  The other lanes read
                 // a clamped address and multiply by their zero window taps.
                 const float2 sv = lds64(l < 8 ? xs + 32 * 4 * 12 : xs);
@@ -347,6 +376,7 @@ logmel2_kernel(const __grid_constant__ FeSegs segs, const __grid_constant__ FeMe
         // ================================================================= mel + log: lane = frame
         const uint32_t stg = stage_u32 + static_cast<uint32_t>((iter & 1) * kStageBytes);
         {
+            const float in_scale = cur.pcm16 ? 3.0517578125e-05f : 1.0f;     // 2^-15
             const uint32_t mp = mag_u32 + static_cast<uint32_t>(lane * kMagStride * 4);
             const int m_end = mel.warp_band[warp + 1];
             for (int m = mel.warp_band[warp]; m < m_end; ++m) {
@@ -361,7 +391,7 @@ logmel2_kernel(const __grid_constant__ FeSegs segs, const __grid_constant__ FeMe
                     acc = fmaf(x.z, w.z, acc);
                     acc = fmaf(x.w, w.w, acc);
                 }
-                const float val = log_fast(acc + 0.001f);
+                const float val = log_fast(fmaf(acc, in_scale, 0.001f));
                 const int col = m & 31;
                 const uint32_t addr = stg + static_cast<uint32_t>((m >> 5) * 4096 + lane * 128 +
                                                                  ((((col >> 2) ^ (lane & 7))) << 4) + (col & 3) * 4);
@@ -451,7 +481,7 @@ cudaError_t launch_logmel_segs(const LogmelSeg* segs, int n_segs, const Frontend
         s.row_begin = segs[i].row_begin;
         s.n_rows = segs[i].n_rows;
         s.tile_begin = tiles;
-        s.pad_ = 0;
+        s.fmt = segs[i].fmt;
         tiles += (segs[i].n_rows + kTileFrames - 1) / kTileFrames;
     }
     if (fs.n == 0) return cudaSuccess;

@@ -70,8 +70,6 @@ struct F3Params {
     int in_stages, in_stride;   // input ring depth, bytes between slots
     int b_slots;
     int prefetch_boxes;      // how far the L2 prefetch cursor runs ahead of the loads (0 = off)
-    int epi_bufs;            // staging blocks per epilogue warp (1 or 2: the second lets a TMA store drain behind the next block)
-    int dbg;                 // BD_F3_DBG experiment bits: 1 no stencil math, 2 no MMAs, 4 no epilogue work (results are garbage)
     int nohalo;              // 1: boxes hold whole patches without the padding ring; the stencil masks its border taps
     int H, W;                // input extent per patch
     int items;               // stencil blocks per box (x 8 channel quads)
@@ -149,7 +147,7 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* a_base = smem;                                            // [2][planes][16 KB]
     unsigned char* epi_base = a_base + kAStages * kAStageBytes;              // [4 warps][4 KB], 1024-byte aligned
-    unsigned char* b_base = epi_base + kEpiBytes * prm.epi_bufs;             // [b_slots][planes][8 KB]
+    unsigned char* b_base = epi_base + kEpiBytes;                            // [b_slots][planes][8 KB]
     unsigned char* in_ring = b_base + prm.b_slots * kBSlotBytes;             // [in_stages][in_stride]
     uint64_t* bars = reinterpret_cast<uint64_t*>(in_ring + prm.in_stages * prm.in_stride);
     uint64_t* a_full = bars;                            // [2]
@@ -341,7 +339,6 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
                         if (elect_one()) {
 #pragma unroll
                             for (int k = 0; k < kBK / 16; ++k) {
-                                if (prm.dbg & 2) break;
                                 const uint64_t koff = static_cast<uint64_t>(k) * 2u;     // 16 fp16 = 32 bytes, >> 4
                                 const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
                                 if (CTA2) {
@@ -358,7 +355,7 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
                                     }
                                 }
                             }
-                            if (NSPLIT == 2 && !CTA2 && !(prm.dbg & 2)) {
+                            if (NSPLIT == 2 && !CTA2) {
                                 // both correction products as one e5m2 contraction over the second planes (K = 128 bytes)
                                 constexpr uint32_t idesc8 = umma_idesc_e5m2(kBM, kMmaN);
 #pragma unroll
@@ -442,7 +439,7 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
                     const uint32_t part_row = static_cast<uint32_t>(part * prm.rows_per_part);
 #pragma unroll 1
                     for (int k = 0; k < 2; ++k) {
-                        if (!blk_ok[k] || (prm.dbg & 1)) break;
+                        if (!blk_ok[k]) break;
                         const uint32_t base = tile + blk_in[k];
                         float4 acc[2][BWc];
 #pragma unroll
@@ -492,9 +489,7 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
     } else if (warp >= 4) {
         // ================================================================= epilogue
         const int q = warp & 3;
-        const uint32_t stg0 = smem_u32(epi_base) + static_cast<uint32_t>(q * kEpiBufBytes * prm.epi_bufs);
-        const bool two_bufs = prm.epi_bufs == 2;
-        uint32_t which = 0;
+        const uint32_t stg = smem_u32(epi_base) + static_cast<uint32_t>(q * kEpiBufBytes);
         const int live = prm.valid_rows - q * 32;       // rows of this warp's lane quad that exist (<= 0: none)
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -510,18 +505,13 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
             mbar_wait_sleepy(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * NACC);
-            if (live > 0 && !(prm.dbg & 4)) {
+            if (live > 0) {
 #pragma unroll 1
                 for (int c0 = 0; c0 < NACC; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), r);
                     const float* bp = biasp.v + n0 + c0;
-                    const uint32_t stg = stg0 + which * kEpiBufBytes;
-                    if (two_bufs) which ^= 1u;
-                    if (lane == 0) {                                   // the store that last read this buffer is done
-                        if (two_bufs) tma_store_wait_read<1>();
-                        else tma_store_wait_read<0>();
-                    }
+                    if (lane == 0) tma_store_wait_read<0>();          // previous block's store has read the buffer
                     __syncwarp();
                     tmem_ld_wait();
 #pragma unroll
@@ -709,18 +699,13 @@ cudaError_t launch_sep_fused3(const PwGemmPlan& p, const float* X, const float* 
     if (nacc > nacc_cap && (nacc_cap == 128 || nacc_cap == 256) && p.N % nacc_cap == 0) nacc = nacc_cap;
     if (nacc != 128 && nacc != 256 && nacc != 512) return cudaErrorInvalidValue;
     const int planes = p.nsplit == 1 ? 1 : 2;
-    // experiment knobs: BD_F3_EPI2=1 double-buffers the epilogue staging (16 KB more), BD_F3_BSLOTS=n sets the weight ring
-    static const int epi2_env = [] { const char* e = getenv("BD_F3_EPI2"); return e ? atoi(e) : 0; }();
-    static const int bslots_env = [] { const char* e = getenv("BD_F3_BSLOTS"); return e ? atoi(e) : 0; }();
-    const int epi_bufs = epi2_env ? 2 : 1;
-    const int fixed = 1024 + kAStages * planes * kATile + kEpiBytes * epi_bufs + kBarBytes;
+    const int fixed = 1024 + kAStages * planes * kATile + kEpiBytes + kBarBytes;
     const int b_slot_bytes = planes * kBSlotPlane;
     // weight ring: enough 16 KB slots in flight to cover the L2 round trip at the MMA's consumption rate (the wider
     // the accumulator, the more slots one k-block eats); the rest of shared memory is the input ring
     // Measured (profiles/r1_summary.md): fewer, larger boxes beat a deeper ring of small ones (per-box barrier and
     // tap-weight reload cost), and shared memory left to L1 matters because the tap weights are re-read per box.
     int b_slots = nacc == 512 ? 3 : 2;
-    if (bslots_env >= 2 && bslots_env <= kMaxBSlots) b_slots = bslots_env;
     const int ring_bytes = kSmemMax - fixed - b_slots * b_slot_bytes;
     F3Params prm;
     if (!plan_geometry(p.K, p.N, H, W, stride, 40 * 1024, &prm)) return cudaErrorInvalidValue;
@@ -735,9 +720,6 @@ cudaError_t launch_sep_fused3(const PwGemmPlan& p, const float* X, const float* 
     if (in_stages < 2) return cudaErrorInvalidValue;
     prm.b_slots = b_slots;
     prm.in_stages = in_stages;
-    prm.epi_bufs = epi_bufs;
-    static const int dbg_env = [] { const char* e = getenv("BD_F3_DBG"); return e ? atoi(e) : 0; }();
-    prm.dbg = dbg_env;
     {
         // Measured on B200: asking L2 for the boxes ahead of time does not help (layers 3-6 within +-2 %, layer 3
         // slower) -- the ring is not what these kernels wait on.  Kept as an experiment knob, off by default.

@@ -50,6 +50,32 @@ def test_coalesced_batches_are_bit_identical_to_single_chunks(engines, hop):
         assert np.array_equal(a, a1) and np.array_equal(emb, emb1)
 
 
+def test_int16_pcm_straight_into_the_frontend_equals_converting_first(engines):
+    """16 kHz mono int16 chunks skip the conversion pass: the frontend transforms the integer values and scales the mel
+    sums by 2^-15 (LogmelSeg::fmt = 1).  Same bits as soundfile's float32 (s / 32768, src/stream/audio.py:22-30) through
+    the float entry -- for whole tiles (TMA), ragged tails (guarded loads), one chunk and coalesced chunks."""
+    e = engines("fp16x3", early_patches=64, late_patches=128, n_slots=8)
+    rng = np.random.default_rng(11)
+    pcms = []
+    for i, n in enumerate([16000 * 30, 16000 * 7 + 123, 15600, 16000 * 41 + 8, 401]):
+        x = O.synth_audio(n, seed=90 + i)
+        pcms.append(np.clip(np.rint(x * 30000 + rng.integers(-3, 4, n)), -32768, 32767).astype(np.int16))
+    want = [e.predict(p.astype(np.float32) / np.float32(32768.0), 96) for p in pcms]
+    got1 = [e.predict_pcm(p, 16000, 96) for p in pcms]
+    e.set_auto_flush(False)
+    try:
+        tks = [e.submit_pcm(p, 16000, 96) for p in pcms]
+        got2 = [t.result() for t in tks]
+    finally:
+        e.set_auto_flush(True)
+    for w, g1, g2 in zip(want, got1, got2):
+        assert g1.shape == w.shape and np.array_equal(g1, w)
+        assert np.array_equal(g2, w)
+    # the log-mel rows themselves (debug entry takes float32): compare through stage 0 of a float chunk
+    lm = e.debug_logmel(pcms[0].astype(np.float32) / np.float32(32768.0), 200)
+    assert np.isfinite(lm).all()
+
+
 def test_coalesced_pcm_chunks_and_overflowing_batches(engines):
     """int16 PCM chunks at two source rates, more patches than one late batch holds: the flush splits them into several
     batches; results equal the one-at-a-time results."""
