@@ -419,38 +419,60 @@ __global__ void __launch_bounds__(256) pw_simt_kernel(const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------ pool + head
-// one CTA per patch, 256 threads x 4 channels = 1024 embedding dims.
-__global__ void __launch_bounds__(256) pool_head_kernel(const float* __restrict__ y, int rows, const float* __restrict__ Wh,
+// Global average pool over the rows of a patch (sum in row order, then / rows: tf.reduce_mean of the graph) and the
+// Dense(n_classes) head, yamnet.py:96-101 + models/model_general_v3/model.py:16,29.
+// Persistent CTAs of 256 threads x 4 channels = 1024 embedding dims walk the patches: the thread's slice of the head
+// matrix (4 x n_classes weights) is loaded once into registers, and the rows of the NEXT patch are in flight while the
+// current one is reduced (one CTA per patch re-read the strided head weights for every patch and sat at 1.3 TB/s).
+template <int NC>
+__global__ void __launch_bounds__(256) pool_head_kernel(const float* __restrict__ y, int P, int rows, const float* __restrict__ Wh,
                                                         const float* __restrict__ bh, int n_classes,
                                                         float* __restrict__ emb, float* __restrict__ act) {
-    __shared__ float red[8][kMaxClasses];
-    const long long p = blockIdx.x;
+    constexpr int kMaxRows = 8;
+    __shared__ float red[2][8][NC];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const float* yp = y + p * rows * kEmb + t * 4;
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < rows; ++r) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(yp + static_cast<long long>(r) * kEmb));
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-    }
+    float w[4][NC];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NC; ++j) w[i][j] = j < n_classes ? __ldg(Wh + static_cast<long long>(t * 4 + i) * n_classes + j) : 0.f;
+    const float bias = t < n_classes ? __ldg(bh + t) : 0.f;
     const float d = static_cast<float>(rows);
-    s.x /= d; s.y /= d; s.z /= d; s.w /= d;
-    if (emb != nullptr) *reinterpret_cast<float4*>(emb + p * kEmb + t * 4) = s;
-    for (int j = 0; j < n_classes; ++j) {
-        const float* wj = Wh + static_cast<long long>(t) * 4 * n_classes + j;
-        float a = s.x * __ldg(wj);
-        a = fmaf(s.y, __ldg(wj + n_classes), a);
-        a = fmaf(s.z, __ldg(wj + 2 * n_classes), a);
-        a = fmaf(s.w, __ldg(wj + 3 * n_classes), a);
+    float4 v[kMaxRows];
+    auto load = [&](long long p) {
+        const float* yp = y + p * rows * kEmb + t * 4;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) red[warp][j] = a;
-    }
-    __syncthreads();
-    if (t < n_classes) {
-        float a = 0.f;
+        for (int r = 0; r < kMaxRows; ++r)
+            if (r < rows) v[r] = __ldg(reinterpret_cast<const float4*>(yp + static_cast<long long>(r) * kEmb));
+    };
+    long long p = blockIdx.x;
+    if (p < P) load(p);
+    int buf = 0;
+    for (; p < P; p += gridDim.x, buf ^= 1) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int wi = 0; wi < 8; ++wi) a += red[wi][t];
-        act[p * n_classes + t] = a + bh[t];
+        for (int r = 0; r < kMaxRows; ++r)
+            if (r < rows) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+        if (p + gridDim.x < P) load(p + gridDim.x);                 // next patch's rows fly behind the reduction
+        s.x /= d; s.y /= d; s.z /= d; s.w /= d;
+        if (emb != nullptr) *reinterpret_cast<float4*>(emb + p * kEmb + t * 4) = s;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            float a = s.x * w[0][j];
+            a = fmaf(s.y, w[1][j], a);
+            a = fmaf(s.z, w[2][j], a);
+            a = fmaf(s.w, w[3][j], a);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) red[buf][warp][j] = a;
+        }
+        __syncthreads();                                            // red[buf] complete; red[buf ^ 1] is free again
+        if (t < n_classes) {
+            float a = 0.f;
+#pragma unroll
+            for (int wi = 0; wi < 8; ++wi) a += red[buf][wi][t];
+            act[p * n_classes + t] = a + bias;
+        }
     }
 }
 
@@ -564,7 +586,11 @@ cudaError_t launch_pool_head(const float* y, int P, int rows_per_patch, const fl
                              int n_classes, float* emb, float* act, cudaStream_t stream) {
     if (P <= 0) return cudaSuccess;
     if (n_classes > kMaxClasses || n_classes < 1) return cudaErrorInvalidValue;
-    pool_head_kernel<<<P, 256, 0, stream>>>(y, rows_per_patch, Wh, bh, n_classes, emb, act);
+    if (rows_per_patch > 8) return cudaErrorInvalidValue;
+    static const int num_sms = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
+    const int grid = P < num_sms * 2 ? P : num_sms * 2;
+    if (n_classes <= 16) pool_head_kernel<16><<<grid, 256, 0, stream>>>(y, P, rows_per_patch, Wh, bh, n_classes, emb, act);
+    else pool_head_kernel<kMaxClasses><<<grid, 256, 0, stream>>>(y, P, rows_per_patch, Wh, bh, n_classes, emb, act);
     return cudaGetLastError();
 }
 
