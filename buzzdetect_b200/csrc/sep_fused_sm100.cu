@@ -466,11 +466,23 @@ sep_fused3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_const
                             }
                         }
                         const uint32_t row0 = part_row + blk_row[k];
+                        // Whole-patch tiles (Wo = 4): the four blocks of a warp start 8 A-tile rows apart, so their
+                        // stores would meet in the same banks (row & 7 and the swizzle equal: 4 wavefronts instead of
+                        // 2 per STS.64).  Odd 8-lane groups therefore store their second output row first.
+                        const bool swap_rows = NOHALO && ((lane >> 3) & 1);
 #pragma unroll
                         for (int o = 0; o < 2; ++o)
 #pragma unroll
-                            for (int r = 0; r < BWc; ++r)
-                                store_a<NSPLIT>(a_hi, a_lo, row0 + static_cast<uint32_t>(o * Wo + r), chunk, half8, c8chunk, c8off, acc[o][r]);
+                            for (int r = 0; r < BWc; ++r) {
+                                float4 val = acc[o][r];
+                                if (NOHALO) {
+                                    const float4 alt = acc[o ^ 1][r];
+                                    val.x = swap_rows ? alt.x : val.x; val.y = swap_rows ? alt.y : val.y;
+                                    val.z = swap_rows ? alt.z : val.z; val.w = swap_rows ? alt.w : val.w;
+                                }
+                                const uint32_t oo = NOHALO ? (static_cast<uint32_t>(o) ^ (swap_rows ? 1u : 0u)) : static_cast<uint32_t>(o);
+                                store_a<NSPLIT>(a_hi, a_lo, row0 + oo * static_cast<uint32_t>(Wo) + static_cast<uint32_t>(r), chunk, half8, c8chunk, c8off, val);
+                            }
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&in_empty[is]);               // box consumed (release orders the reads)
