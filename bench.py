@@ -507,6 +507,12 @@ def run_ours(args, rank, world, local):
                 "chunks_per_pass": round((c1 - c0) / max(b1 - b0, 1), 2), "passes": int(b1 - b0),
                 "wall_s": dt, "inferer_loop_s": plugin_run.submit_s}
 
+    def with_h2d_rate(d):
+        """host->device GB/s this leg sustained, summed over the ranks (what a shared host has to deliver)."""
+        if d.get("h2d_bytes_per_step"):
+            d["h2d_gbs_all_gpus"] = d["h2d_bytes_per_step"] * d["value"] / hours_per_step / 1e9
+        return d
+
     d2h_bytes = sum(capi.frames_for(m, HOP_FRAMES)[2] for _, m in bounds) * eng.n_classes * 4
     e2e_pcm16 = timed_plugin("pcm16", args.steps)
     e2e_pcm16.update({"h2d_bytes_per_step": n * 2, "d2h_bytes_per_step": d2h_bytes, "chunk_s": args.chunk_s,
@@ -517,6 +523,8 @@ def run_ours(args, rank, world, local):
     e2e_plugin.update({"h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": d2h_bytes, "chunk_s": args.chunk_s,
                        "chunks_per_step": len(bounds), "entry": "load_model('model_general_v3').predict(float32 chunk) per chunk, "
                        "pinned float32 samples (the reference streamer's dtype): 230 MB per audio-hour over PCIe"})
+    with_h2d_rate(e2e_pcm16)
+    with_h2d_rate(e2e_plugin)
     pageable = np.array(hv, copy=True)
     e2e_pageable = timed_plugin("pageable", max(1, args.steps // 2))
     e2e_pageable.update({"h2d_bytes_per_step": n * 4, "entry": "the same with pageable numpy input (host->device copies are "
@@ -635,7 +643,7 @@ def run_ours(args, rank, world, local):
     total_prof_ms = sum(prof[k]["ms"] for k in ("frontend", "conv1", "depthwise", "pointwise", "pool_head"))
     traffic_tab = {}
     import glob
-    tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_*.json")), key=os.path.getmtime)
+    tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_*.json")))      # tags sort by round: r1 < r1e < r2
     if tfiles:
         with open(tfiles[-1]) as f:
             traffic_tab = json.load(f)

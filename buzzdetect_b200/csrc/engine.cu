@@ -642,6 +642,26 @@ int launch_pending(bd_engine* e, bool only_arrived) {
             ++pos;
             if (g >= e->S2) break;
         }
+        if (only_arrived && group.size() >= 6) {
+            // Quantisation-aware pass size: the 6x4 layers (8-12, 30 % of a pass) run one 5-patch tile per SM and round,
+            // so a pass whose tile count sits just above a multiple of the SM count pays a whole extra round for a
+            // few tiles.  Up to two trailing chunks are left for the next pass when that fills the rounds better
+            // (they are at the head of the queue then, so nothing is deferred twice).
+            auto fill = [&](int64_t patches) {
+                const int64_t tiles = (patches + 4) / 5;
+                const int64_t rounds = (tiles + e->num_sms - 1) / e->num_sms;
+                return static_cast<double>(tiles) / static_cast<double>(rounds * e->num_sms);
+            };
+            int64_t pk = g;
+            double best = fill(g);
+            int drop = 0;
+            for (int k = 1; k <= 2; ++k) {
+                pk -= e->slots[group[group.size() - k]].P + tail_slots;
+                const double f = fill(pk);
+                if (f > best + 0.03) { best = f; drop = k; }
+            }
+            for (int k = 0; k < drop; ++k) { group.pop_back(); outs.pop_back(); --pos; }
+        }
         rc = launch_group(e, group, outs);
         for (int si : group) e->slots[si].state = rc == 0 ? 2 : 0;
         if (only_arrived) break;

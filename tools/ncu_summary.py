@@ -19,6 +19,7 @@ COLS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
         'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
         'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'lts__t_sector_hit_rate.pct',
@@ -29,6 +30,8 @@ def family(short: str) -> str:
     if short.startswith('sep_fused3_kernel'):
         m = re.search(r'<\s*\d+,\s*\d+,\s*(\d+)', short)
         return 'sep_fused3_kernel[layers 8-12, tensor]' if m and m.group(1) == '512' else 'sep_fused3_kernel[layers 3-7, hbm]'
+    if short.startswith('logmel2_kernel'):
+        return 'logmel_kernel'
     for nm in ('pw_gemm_kernel', 'depthwise_kernel', 'l12_fused2_kernel', 'logmel_kernel', 'conv1_dw2_kernel',
                'pool_head_kernel', 'resample_tc_kernel', 'resample_kernel'):
         if short.startswith(nm):
@@ -47,7 +50,7 @@ def main():
     with open(out, 'w', newline='') as f:
         w = csv.writer(f)
         w.writerow(['launch', 'kernel'] + COLS)
-        w.writerow(['', ''] + ['us', 'Mbyte', 'Mbyte'] + ['%'] * 5 + ['register/thread', '%', '%', '%', '', ''])
+        w.writerow(['', ''] + ['us', 'Mbyte', 'Mbyte'] + ['%'] * 6 + ['register/thread', '%', '%', '%', '', ''])
         n = 0
         for src in srcs:                                  # every capture file carries its own units row
             rows = list(csv.reader(open(src)))
