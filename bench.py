@@ -363,6 +363,26 @@ def run_extra_configs(args, rank, world, dev, eng, model, d_x, d_act, n, hv, use
                 "199.68 s chunks through predict_pcm (downmix + tcgen05 resampler + path on the device); the resume run "
                 "is a parity test (tests/test_writer_pipeline.py), not a timing"}
     del feed3, pcm3
+    # ---- config 1 / configs[0]: the reference's own audio_in/testbuzz.mp3 (6.55 s, 32 kHz mono; PCM fixture of its decode):
+    # one file = one 7-patch chunk, so this is the latency of a single small pass, resampler included
+    fx = os.path.join(ROOT, "tests", "golden", "testbuzz_32k_s16.wav")
+    if rank == 0 and os.path.exists(fx):
+        import wave
+        with wave.open(fx, "rb") as w:
+            sr1, nfr = w.getframerate(), w.getnframes()
+            raw = np.frombuffer(w.readframes(nfr), dtype=np.int16).copy()
+        pin1 = capi.pinned_empty(raw.size, np.int16)
+        pin1[:] = raw
+        for _ in range(5):
+            rows = model.predict_pcm(pin1, sr1).numpy().shape[0]
+        t0 = time.perf_counter()
+        reps = 50
+        for _ in range(reps):
+            model.predict_pcm(pin1, sr1).numpy()
+        dt = (time.perf_counter() - t0) / reps
+        out["cfg1_testbuzz"] = {"ms_per_file": dt * 1e3, "value": (nfr / sr1 / 3600.0) / dt, "unit": UNIT, "rows": int(rows),
+                                "what": "BASELINE configs[0]: testbuzz.mp3 as decoded PCM (32 kHz mono int16, 6.55 s), one "
+                                        "synchronous predict_pcm(...).numpy() per file: latency of one 7-patch pass"}
     return out
 
 
