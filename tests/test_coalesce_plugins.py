@@ -76,6 +76,39 @@ def test_int16_pcm_straight_into_the_frontend_equals_converting_first(engines):
     assert np.isfinite(lm).all()
 
 
+def test_int16_direct_path_half_hop_and_trace(engines):
+    """Half hop (overlapping patches, one spare slot between coalesced chunks) over int16 chunks, with the slot-API
+    timeline switched on: the trace reports every submit, input copy, pass and result copy in order."""
+    e = engines("fp16x3", early_patches=64, late_patches=256, n_slots=16)
+    pcms = [np.clip(np.rint(O.synth_audio(n, seed=70 + i) * 25000), -32768, 32767).astype(np.int16)
+            for i, n in enumerate([16000 * 11, 16000 * 5 + 3, 15600 + 7680, 16000 * 23 + 11, 16000 * 2, 16000 * 9,
+                                   16000 * 14 + 160, 16000 * 6])]
+    want = [e.predict(p.astype(np.float32) / np.float32(32768.0), 48) for p in pcms]
+    e.trace(True)
+    e.set_auto_flush(False)
+    try:
+        tks = [e.submit_pcm(p, 16000, 48) for p in pcms]
+        got = [t.result() for t in tks]
+    finally:
+        e.set_auto_flush(True)
+    recs = e.trace(False)
+    for g, w in zip(got, want):
+        assert g.shape == w.shape and np.array_equal(g, w)
+    kinds = [r[0] for r in recs]
+    assert kinds.count(0) == len(pcms) and kinds.count(1) == len(pcms)          # submits, input copies
+    assert kinds.count(4) == len(pcms) and kinds.count(5) == len(pcms)          # result copies, waits
+    assert kinds.count(2) == kinds.count(3) >= 1                                # passes begin / end
+    begins = [r for r in recs if r[0] == 2]
+    assert sum(r[2] for r in begins) == len(pcms)                               # every chunk rode in exactly one pass
+    dev = {(r[0], r[1]): r[4] for r in recs if r[4] >= 0}
+    for r in begins:
+        assert dev[(3, r[1])] >= r[4]                                           # a pass ends after it begins
+    # auto mode with many chunks queued at once exercises the quantisation-aware pass sizing; results stay identical
+    tks = [e.submit_pcm(p, 16000, 48) for p in pcms * 2]
+    for t, w in zip(tks, want * 2):
+        assert np.array_equal(t.result(), w)
+
+
 def test_coalesced_pcm_chunks_and_overflowing_batches(engines):
     """int16 PCM chunks at two source rates, more patches than one late batch holds: the flush splits them into several
     batches; results equal the one-at-a-time results."""
