@@ -50,7 +50,7 @@ HOP_FRAMES = 96
 PW_FLOP_PER_PATCH = 132_120_576
 DW_BYTES_PER_PATCH = 2_445_312
 FRONTEND_BYTES_PER_PATCH = 86_016
-FE_WARP_INSTR_PER_FRAME = 450          # logmel2_kernel: 707 SASS instructions per two-frame FFT round + the mel phase
+FE_WARP_INSTR_PER_FRAME = 523          # logmel2_kernel: smsp__inst_executed.sum / frames in profiles/ncu_r2_kernels (188.4 M / 360,000)
 TOTAL_FLOP_PER_PATCH = 137_289_728
 METRIC = "audio-hours processed/sec (realtime factor) at 1/2/4/8 B200 vs host-CPU ref"
 UNIT = "audio-hours/s"
@@ -686,6 +686,39 @@ def run_ours(args, rank, world, local):
         if tens:
             rooflines[nm]["executed_mma_factor"] = mma_factor
             rooflines[nm]["hbm_gbs"] = f["bytes"] / (f["ms"] / 1e3) / 1e9
+    # what ncu saw of the SM's shared-memory data pipe (one 128-byte wavefront per clock, shared by LDS/STS/LDG hits and
+    # the tensor core's operand fetch): the bound of the fused kernels that neither HBM nor the tensor pipe explains
+    kfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_r*_kernels.csv")))
+    if kfiles:
+        import csv
+        import re as _re
+        with open(kfiles[-1]) as f:
+            rows = list(csv.reader(f))
+        hdr = rows[0]
+        c_l = "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"
+        c_t = "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"
+        if c_l in hdr and c_t in hdr:
+            acc = {}
+            for r in rows[2:]:
+                nm = r[1]
+                if nm.startswith("sep_fused3_kernel"):
+                    m = _re.search(r"<\s*\d+,\s*\d+,\s*(\d+)", nm)
+                    key = "sep_fused3_kernel[layers 8-12, tensor]" if m and m.group(1) == "512" else "sep_fused3_kernel[layers 3-7, hbm]"
+                elif nm.startswith("logmel"):
+                    key = "logmel_kernel"
+                else:
+                    key = _re.sub(r"<.*", "", nm)
+                try:
+                    a = acc.setdefault(key, [0.0, 0.0, 0])
+                    a[0] += float(r[hdr.index(c_l)]); a[1] += float(r[hdr.index(c_t)]); a[2] += 1
+                except ValueError:
+                    pass
+            for key, (l, t, cnt) in acc.items():
+                if key in rooflines and cnt:
+                    rooflines[key]["smem_pipe_pct"] = {"lsu_wavefronts": l / cnt, "tensor_operand_wavefronts": t / cnt,
+                                                      "note": "ncu, % of the one-wavefront-per-clock L1/shared data pipe; TMA writes "
+                                                              "into shared memory use the same pipe and are in neither counter",
+                                                      "source": os.path.basename(kfiles[-1])}
     dominant = max(rooflines, key=lambda k: rooflines[k]["ms"])
     roofline = dict(rooflines[dominant])
     roofline["kernel"] = dominant
@@ -704,8 +737,9 @@ def run_ours(args, rank, world, local):
         sm_clock_hz = (clocks or {}).get("sm_mhz") or 1965.0
         ideal_ms = warp_instr / (148 * 4 * sm_clock_hz * 1e6) * 1e3
         fe["issue_bound"] = {"warp_instructions_per_frame": FE_WARP_INSTR_PER_FRAME, "ideal_ms_at_4_ipc_per_sm": ideal_ms,
-                             "frac": ideal_ms / fe["ms"], "note": "512-point fp32 FFT + split + mel: SASS instruction count "
-                             "of logmel2_kernel per frame against one instruction per scheduler per clock"}
+                             "frac": ideal_ms / fe["ms"], "note": "512-point fp32 FFT + split + mel: executed warp instructions "
+                             "per frame (ncu) against one instruction per scheduler per clock; the FMA pipe alone (about 300 of "
+                             "them, FFMA = 1.04 clk per scheduler, tools/ubench/ffma2.cu) puts the floor near 0.14 ms per audio-hour"}
 
     if rank == 0:
         from buzzdetect_b200 import probe
