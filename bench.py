@@ -470,7 +470,7 @@ def run_ours(args, rank, world, local):
     from buzzdetect_b200.inference.models import load_model
     framehop_prop = HOP_FRAMES / 96.0
     model = load_model("model_general_v3", framehop_prop=framehop_prop, initialize=True)
-    pcm16 = capi.pinned_empty(n, np.int16)
+    pcm16 = capi.pinned_empty(n, np.int16, write_combined=args.wc)
     pcm16[:] = np.clip(np.rint(hv * 32768.0), -32768, 32767).astype(np.int16)
     chunk_n = int(round(args.chunk_s * SR))
     bounds = [(o, min(chunk_n, n - o)) for o in range(0, n, chunk_n)]
@@ -802,6 +802,7 @@ def main():
                     help="chunk length of the raw bd_submit_host leg")
     ap.add_argument("--slots", type=int, default=48, help="chunks in flight through the plugin (engine slots)")
     ap.add_argument("--no-configs", dest="no_configs", action="store_true", help="skip the configs 3 / 5 legs")
+    ap.add_argument("--wc", action="store_true", help="experiment: write-combined pinned memory for the int16 feed")
     ap.add_argument("--early", type=int, default=0)
     ap.add_argument("--late", type=int, default=0)
     ap.add_argument("--fuse-mask", dest="fuse_mask", type=int, default=-1,
