@@ -24,6 +24,7 @@
 //
 // A launch covers a table of segments (independent chunks of audio, each framed and padded on its own, exactly as the
 // reference treats chunks): segment s writes log-mel rows [row_begin, row_begin + n_rows) of one shared buffer.
+#include <cstdlib>
 #include <cstring>
 
 #include "bd_common.cuh"
@@ -59,6 +60,7 @@ struct FeMel {                     // kernel parameter (constant bank): uniform 
     int glen[kMel];                // number of groups
     int goff[kMel];                // index of the band's first group in w4
     int warp_band[kFeWarps + 1];   // warp w computes bands [warp_band[w], warp_band[w+1]) (balanced by work)
+    int static_ok;                 // the matrix has the sparsity structure mel_layout.inc was generated for
 };
 
 struct FeSeg {
@@ -194,6 +196,27 @@ struct TileInfo {
     bool pcm16;            // the tile holds int16 PCM: the FFT runs on the integer values, the mel sums are scaled by 2^-15
 };
 
+// ---- the mel phase unrolled for YAMNet's mel structure (tools/gen_mel_layout.py): no loop control, no table look-ups,
+// weights as immediate constant-bank operands of the FMAs, zero-weight lanes skipped
+#define MEL_ARGS const FeMel& mel, uint32_t mp, uint32_t stg, int lane, float in_scale
+#define MEL_LDS(off) lds128(mp + (off))
+#define MEL_W(g) mel.w4[(g)]
+#define MEL_EMIT(m, acc)                                                                                              \
+    do {                                                                                                              \
+        const float val_ = log_fast(fmaf((acc), in_scale, 0.001f));                                                   \
+        constexpr int col_ = (m) & 31;                                                                                \
+        const uint32_t addr_ = stg + static_cast<uint32_t>(((m) >> 5) * 4096 + lane * 128 +                           \
+                                                           ((((col_ >> 2) ^ (lane & 7))) << 4) + (col_ & 3) * 4);      \
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr_), "f"(val_) : "memory");                                   \
+    } while (0)
+template <int W> __device__ __forceinline__ void mel_static_warp(MEL_ARGS);
+#include "mel_layout.inc"
+#undef MEL_EMIT
+#undef MEL_W
+#undef MEL_LDS
+#undef MEL_ARGS
+
+template <bool STATIC_MEL>
 __global__ void __launch_bounds__(kFeThreads, 2)
 logmel2_kernel(const __grid_constant__ FeSegs segs, const __grid_constant__ FeMel mel,
                const __grid_constant__ CUtensorMap map_out, const float* __restrict__ window,
@@ -375,7 +398,20 @@ logmel2_kernel(const __grid_constant__ FeSegs segs, const __grid_constant__ FeMe
         }
         // ================================================================= mel + log: lane = frame
         const uint32_t stg = stage_u32 + static_cast<uint32_t>((iter & 1) * kStageBytes);
-        {
+        if (STATIC_MEL) {
+            const float in_scale = cur.pcm16 ? 3.0517578125e-05f : 1.0f;     // 2^-15
+            const uint32_t mp = mag_u32 + static_cast<uint32_t>(lane * kMagStride * 4);
+            switch (warp) {
+                case 0: mel_static_warp<0>(mel, mp, stg, lane, in_scale); break;
+                case 1: mel_static_warp<1>(mel, mp, stg, lane, in_scale); break;
+                case 2: mel_static_warp<2>(mel, mp, stg, lane, in_scale); break;
+                case 3: mel_static_warp<3>(mel, mp, stg, lane, in_scale); break;
+                case 4: mel_static_warp<4>(mel, mp, stg, lane, in_scale); break;
+                case 5: mel_static_warp<5>(mel, mp, stg, lane, in_scale); break;
+                case 6: mel_static_warp<6>(mel, mp, stg, lane, in_scale); break;
+                default: mel_static_warp<7>(mel, mp, stg, lane, in_scale); break;
+            }
+        } else {
             const float in_scale = cur.pcm16 ? 3.0517578125e-05f : 1.0f;     // 2^-15
             const uint32_t mp = mag_u32 + static_cast<uint32_t>(lane * kMagStride * 4);
             const int m_end = mel.warp_band[warp + 1];
@@ -426,7 +462,9 @@ logmel2_kernel(const __grid_constant__ FeSegs segs, const __grid_constant__ FeMe
 }  // namespace
 
 cudaError_t frontend2_init_device() {
-    return cudaFuncSetAttribute(logmel2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFe2Smem);
+    cudaError_t e = cudaFuncSetAttribute(logmel2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFe2Smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(logmel2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFe2Smem);
 }
 
 bool frontend2_build_mel(const FrontendTables& tab, FrontendMelParam* out_raw) {
@@ -460,6 +498,23 @@ bool frontend2_build_mel(const FrontendTables& tab, FrontendMelParam* out_raw) {
         m.warp_band[w] = b;
     }
     m.warp_band[kFeWarps] = kMel;
+    // does the matrix have the structure the unrolled mel phase was generated for?  (bins per band, and which lanes of
+    // every four-bin group carry weight; a zero INSIDE a band's run would only cost an FMA by zero, never a wrong sum)
+    static_assert(kFeWarps == 8, "mel_layout.inc is generated for eight warps");
+    bool same = groups == kMlGroups;
+    for (int b = 0; same && b < kMel; ++b) {
+        same = m.gbin[b] == kMlGbin[b] && m.glen[b] == kMlGlen[b] && m.goff[b] == kMlGoff[b];
+        for (int g = 0; same && g < m.glen[b]; ++g) {
+            int mask = 0;
+            for (int c = 0; c < 4; ++c) {
+                const int k = m.gbin[b] + 4 * g + c;
+                if (k >= tab.mel_start[b] && k < tab.mel_start[b] + tab.mel_len[b]) mask |= 1 << c;
+            }
+            same = mask == kMlMask[m.goff[b] + g];
+        }
+    }
+    static const int static_env = [] { const char* e = getenv("BD_FE_STATIC_MEL"); return e ? atoi(e) : 1; }();
+    m.static_ok = (same && static_env != 0) ? 1 : 0;
     return true;
 }
 
@@ -490,8 +545,9 @@ cudaError_t launch_logmel_segs(const LogmelSeg* segs, int n_segs, const Frontend
     CUtensorMap map_out;
     if (!encode_store_map_f32(&map_out, logmel, logmel_rows < 32 ? 32 : logmel_rows, kMel, 32)) return cudaErrorUnknown;
     const int grid = tiles < 2 * num_sms ? tiles : 2 * num_sms;
-    logmel2_kernel<<<grid, kFeThreads, kFe2Smem, stream>>>(fs, *reinterpret_cast<const FeMel*>(&mel_raw), map_out, window,
-                                                          logmel);
+    const FeMel& melp = *reinterpret_cast<const FeMel*>(&mel_raw);
+    if (melp.static_ok) logmel2_kernel<true><<<grid, kFeThreads, kFe2Smem, stream>>>(fs, melp, map_out, window, logmel);
+    else logmel2_kernel<false><<<grid, kFeThreads, kFe2Smem, stream>>>(fs, melp, map_out, window, logmel);
     return cudaGetLastError();
 }
 
