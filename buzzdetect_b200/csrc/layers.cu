@@ -191,11 +191,15 @@ __global__ void __launch_bounds__(256) conv1_dw2_kernel(const float* __restrict_
 // (the per-tap version was L1-bandwidth bound: 18 LDG.128 per output vector; this one issues 6.75 for R = 4).
 // Channel-contiguous float4 accesses: consecutive threads take consecutive channel quads of the same strip, so
 // every warp-level load/store touches whole 128-byte lines.
-template <int STRIDE, int R, int OUT_MODE>
-__global__ void __launch_bounds__(256) depthwise_kernel(const float* __restrict__ in, int P, int H, int W, int C,
+// HH / WW / CH > 0 fix the layer's extent at compile time (the three stand-alone layers of YAMNet: 12x8x256, 6x4x512,
+// 3x2x1024): every load offset becomes an immediate and the bounds tests fold away -- the generic instantiation spends
+// a third of its instructions on 64-bit address arithmetic (179 IMAD + 99 IADD3 + 63 LEA against 144 FFMA).
+template <int STRIDE, int R, int OUT_MODE, int HH = 0, int WW = 0, int CH = 0>
+__global__ void __launch_bounds__(256) depthwise_kernel(const float* __restrict__ in, int P, int H_, int W_, int C_,
                                                         const float* __restrict__ w, const float* __restrict__ b,
                                                         float* __restrict__ out_f32, __half* __restrict__ out_hi,
                                                         __half* __restrict__ out_lo) {
+    const int H = HH > 0 ? HH : H_, W = WW > 0 ? WW : W_, C = CH > 0 ? CH : C_;
     // C/4 and Wo/R are powers of two for every YAMNet layer, so (channel quad, strip, row) come from shifts and masks;
     // the only division is one 32-bit block-uniform one.  (64-bit div/mod per thread cost more than the 36 FMAs.)
     const int Ho = H / STRIDE, Wo = W / STRIDE;
@@ -555,6 +559,22 @@ cudaError_t launch_depthwise(const float* in, int P, int H, int W, int C, int st
 #undef BD_DW2
         return cudaGetLastError();
     }
+    // the three stand-alone layers of the default plan, with compile-time extents
+#define BD_DW_FIXED(S, RR, HH, WW, CH)                                                                                   \
+    if (stride == S && R == RR && H == HH && W == WW && C == CH) {                                                       \
+        if (out_mode == 0) depthwise_kernel<S, RR, 0, HH, WW, CH><<<grid, 256, 0, stream>>>(in, P, H, W, C, w, b, out_f32, out_hi, out_lo); \
+        else if (out_mode == 1) depthwise_kernel<S, RR, 1, HH, WW, CH><<<grid, 256, 0, stream>>>(in, P, H, W, C, w, b, out_f32, out_hi, out_lo); \
+        else if (out_mode == 3) depthwise_kernel<S, RR, 3, HH, WW, CH><<<grid, 256, 0, stream>>>(in, P, H, W, C, w, b, out_f32, out_hi, out_lo); \
+        else depthwise_kernel<S, RR, 2, HH, WW, CH><<<grid, 256, 0, stream>>>(in, P, H, W, C, w, b, out_f32, out_hi, out_lo); \
+        return cudaGetLastError();                                                                                       \
+    }
+    static const int fixed_env = [] { const char* e = getenv("BD_DW_FIXED"); return e ? atoi(e) : 1; }();
+    if (fixed_env != 0) {
+        BD_DW_FIXED(2, 4, 12, 8, 256)
+        BD_DW_FIXED(2, 2, 6, 4, 512)
+        BD_DW_FIXED(1, 2, 3, 2, 1024)
+    }
+#undef BD_DW_FIXED
 #define BD_DW(S, RR, MODE) \
     depthwise_kernel<S, RR, MODE><<<grid, 256, 0, stream>>>(in, P, H, W, C, w, b, out_f32, out_hi, out_lo)
 #define BD_DW_MODE(S, RR)                          \
