@@ -50,7 +50,7 @@ HOP_FRAMES = 96
 PW_FLOP_PER_PATCH = 132_120_576
 DW_BYTES_PER_PATCH = 2_445_312
 FRONTEND_BYTES_PER_PATCH = 86_016
-FE_WARP_INSTR_PER_FRAME = 523          # logmel2_kernel: smsp__inst_executed.sum / frames in profiles/ncu_r2_kernels (188.4 M / 360,000)
+FE_WARP_INSTR_PER_FRAME = 417          # logmel2_kernel: smsp__inst_executed.sum / frames (ncu, round 2: 150.3 M / 360,000)
 TOTAL_FLOP_PER_PATCH = 137_289_728
 METRIC = "audio-hours processed/sec (realtime factor) at 1/2/4/8 B200 vs host-CPU ref"
 UNIT = "audio-hours/s"
