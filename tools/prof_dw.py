@@ -1,3 +1,4 @@
+"""Per-stage and per-depthwise-layer device times of one 1-hour pass (CUDA events around every launch): python tools/prof_dw.py"""
 import os,sys
 sys.path.insert(0,".")
 os.environ["BUZZ_B200_ALLOW_SYNTHETIC"]="1"
