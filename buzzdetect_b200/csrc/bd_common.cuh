@@ -347,6 +347,14 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 // significant bits; beyond that hi saturates at fp16's largest finite value (and lo carries what it can) instead of
 // turning into inf.  A real checkpoint's activations are O(1)..O(100); the guard costs one FMNMX per conversion.
 __device__ __forceinline__ __half half_sat(float x) { return __float2half_rn(fminf(x, 65504.f)); }
+// Two values at once: ONE F2FP.SATFINITE.F16.F32.PACK_AB instead of two FMNMX + a packed convert (the hi/lo split was
+// costing as many ALU-pipe instructions as the stencil's FMAs cost FMA-pipe instructions).  Same result as half_sat()
+// on each element for every finite input: saturate to +-65504, round to nearest even.  .x = first, .y = second.
+__device__ __forceinline__ __half2 half2_sat(float first, float second) {
+    uint32_t p;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(second), "f"(first));
+    return *reinterpret_cast<__half2*>(&p);
+}
 
 // ------------------------------------------------------------------------------------------ misc
 __device__ __forceinline__ bool elect_one() {

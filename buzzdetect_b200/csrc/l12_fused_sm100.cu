@@ -215,15 +215,13 @@ l12_fused2_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_con
                         const uint32_t row = static_cast<uint32_t>((2 * brow + o) * 32 + ws * 4 + r);
                         const uint32_t off = (row >> 3) * 1024u + (row & 7u) * 128u + ((chunk ^ (row & 7u)) << 4) +
                                              (static_cast<uint32_t>(quad & 1) << 3);
-                        const __half h0 = half_sat(a.x), h1 = half_sat(a.y);
-                        const __half h2 = half_sat(a.z), h3 = half_sat(a.w);
-                        __half2 hp[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
+                        __half2 hp[2] = {half2_sat(a.x, a.y), half2_sat(a.z, a.w)};
+                        const __half h0 = __low2half(hp[0]), h1 = __high2half(hp[0]);
+                        const __half h2 = __low2half(hp[1]), h3 = __high2half(hp[1]);
                         sts64(a_hi + off, reinterpret_cast<uint32_t*>(hp)[0], reinterpret_cast<uint32_t*>(hp)[1]);
                         if (NSPLIT > 1) {
-                            __half2 lp[2] = {__halves2half2(half_sat(a.x - __half2float(h0)),
-                                                            half_sat(a.y - __half2float(h1))),
-                                             __halves2half2(half_sat(a.z - __half2float(h2)),
-                                                            half_sat(a.w - __half2float(h3)))};
+                            __half2 lp[2] = {half2_sat(a.x - __half2float(h0), a.y - __half2float(h1)),
+                                             half2_sat(a.z - __half2float(h2), a.w - __half2float(h3))};
                             sts64(a_lo + off, reinterpret_cast<uint32_t*>(lp)[0], reinterpret_cast<uint32_t*>(lp)[1]);
                         }
                     }

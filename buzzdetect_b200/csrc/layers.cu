@@ -168,15 +168,13 @@ __global__ void __launch_bounds__(256) conv1_dw2_kernel(const float* __restrict_
                 if (OUT_MODE == 0) {
                     *reinterpret_cast<float4*>(out_f32 + o) = a;
                 } else {
-                    const __half h0 = half_sat(a.x), h1 = half_sat(a.y);
-                    const __half h2 = half_sat(a.z), h3 = half_sat(a.w);
-                    __half2 hp[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
+                    __half2 hp[2] = {half2_sat(a.x, a.y), half2_sat(a.z, a.w)};
+                    const __half h0 = __low2half(hp[0]), h1 = __high2half(hp[0]);
+                    const __half h2 = __low2half(hp[1]), h3 = __high2half(hp[1]);
                     *reinterpret_cast<uint2*>(out_hi + o) = *reinterpret_cast<uint2*>(hp);
                     if (OUT_MODE == 2) {
-                        __half2 lp[2] = {__halves2half2(half_sat(a.x - __half2float(h0)),
-                                                        half_sat(a.y - __half2float(h1))),
-                                         __halves2half2(half_sat(a.z - __half2float(h2)),
-                                                        half_sat(a.w - __half2float(h3)))};
+                        __half2 lp[2] = {half2_sat(a.x - __half2float(h0), a.y - __half2float(h1)),
+                                         half2_sat(a.z - __half2float(h2), a.w - __half2float(h3))};
                         *reinterpret_cast<uint2*>(out_lo + o) = *reinterpret_cast<uint2*>(lp);
                     }
                 }
@@ -260,14 +258,14 @@ __global__ void __launch_bounds__(256) depthwise_kernel(const float* __restrict_
             if (OUT_MODE == 0) {
                 *reinterpret_cast<float4*>(out_f32 + o) = a;
             } else {
-                const __half h0 = half_sat(a.x), h1 = half_sat(a.y);
-                const __half h2 = half_sat(a.z), h3 = half_sat(a.w);
-                __half2 hp[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
+                __half2 hp[2] = {half2_sat(a.x, a.y), half2_sat(a.z, a.w)};
+                const __half h0 = __low2half(hp[0]), h1 = __high2half(hp[0]);
+                const __half h2 = __low2half(hp[1]), h3 = __high2half(hp[1]);
                 *reinterpret_cast<uint2*>(out_hi + o) = *reinterpret_cast<uint2*>(hp);
                 if (OUT_MODE == 2) {
                     __half2 lp[2] = {
-                        __halves2half2(half_sat(a.x - __half2float(h0)), half_sat(a.y - __half2float(h1))),
-                        __halves2half2(half_sat(a.z - __half2float(h2)), half_sat(a.w - __half2float(h3)))};
+                        half2_sat(a.x - __half2float(h0), a.y - __half2float(h1)),
+                        half2_sat(a.z - __half2float(h2), a.w - __half2float(h3))};
                     *reinterpret_cast<uint2*>(out_lo + o) = *reinterpret_cast<uint2*>(lp);
                 }
                 if (OUT_MODE == 3) {
@@ -362,14 +360,14 @@ __global__ void __launch_bounds__(256) depthwise2_kernel(const float* __restrict
                 if (OUT_MODE == 0) {
                     *reinterpret_cast<float4*>(out_f32 + oo) = a;
                 } else {
-                    const __half h0 = half_sat(a.x), h1 = half_sat(a.y);
-                    const __half h2 = half_sat(a.z), h3 = half_sat(a.w);
-                    __half2 hp[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
+                    __half2 hp[2] = {half2_sat(a.x, a.y), half2_sat(a.z, a.w)};
+                    const __half h0 = __low2half(hp[0]), h1 = __high2half(hp[0]);
+                    const __half h2 = __low2half(hp[1]), h3 = __high2half(hp[1]);
                     *reinterpret_cast<uint2*>(out_hi + oo) = *reinterpret_cast<uint2*>(hp);
                     if (OUT_MODE == 2) {
                         __half2 lp[2] = {
-                            __halves2half2(half_sat(a.x - __half2float(h0)), half_sat(a.y - __half2float(h1))),
-                            __halves2half2(half_sat(a.z - __half2float(h2)), half_sat(a.w - __half2float(h3)))};
+                            half2_sat(a.x - __half2float(h0), a.y - __half2float(h1)),
+                            half2_sat(a.z - __half2float(h2), a.w - __half2float(h3))};
                         *reinterpret_cast<uint2*>(out_lo + oo) = *reinterpret_cast<uint2*>(lp);
                     }
                 }

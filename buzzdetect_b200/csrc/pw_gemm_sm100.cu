@@ -422,15 +422,13 @@ sep_fused_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_cons
                         const int row = strip * R + r;
                         const uint32_t off = static_cast<uint32_t>((row >> 3) * 1024 + (row & 7) * 128 +
                                                                    ((((quad >> 1) ^ (row & 7))) << 4) + ((quad & 1) << 3));
-                        const __half h0 = half_sat(a.x), h1 = half_sat(a.y);
-                        const __half h2 = half_sat(a.z), h3 = half_sat(a.w);
-                        __half2 hp[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
+                        __half2 hp[2] = {half2_sat(a.x, a.y), half2_sat(a.z, a.w)};
+                        const __half h0 = __low2half(hp[0]), h1 = __high2half(hp[0]);
+                        const __half h2 = __low2half(hp[1]), h3 = __high2half(hp[1]);
                         *reinterpret_cast<uint2*>(a_hi + off) = *reinterpret_cast<uint2*>(hp);
                         if (NSPLIT > 1) {
-                            __half2 lp[2] = {__halves2half2(half_sat(a.x - __half2float(h0)),
-                                                            half_sat(a.y - __half2float(h1))),
-                                             __halves2half2(half_sat(a.z - __half2float(h2)),
-                                                            half_sat(a.w - __half2float(h3)))};
+                            __half2 lp[2] = {half2_sat(a.x - __half2float(h0), a.y - __half2float(h1)),
+                                             half2_sat(a.z - __half2float(h2), a.w - __half2float(h3))};
                             *reinterpret_cast<uint2*>(a_lo + off) = *reinterpret_cast<uint2*>(lp);
                         }
                     }
@@ -638,15 +636,13 @@ l12_fused_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_cons
                 const int row = orow * 32 + ws * 2 + r;
                 const uint32_t off = static_cast<uint32_t>((row >> 3) * 1024 + (row & 7) * 128 +
                                                            ((((cg >> 1) ^ (row & 7))) << 4) + ((cg & 1) << 3));
-                const __half h0 = half_sat(a.x), h1 = half_sat(a.y);
-                const __half h2 = half_sat(a.z), h3 = half_sat(a.w);
-                __half2 hp[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
+                __half2 hp[2] = {half2_sat(a.x, a.y), half2_sat(a.z, a.w)};
+                const __half h0 = __low2half(hp[0]), h1 = __high2half(hp[0]);
+                const __half h2 = __low2half(hp[1]), h3 = __high2half(hp[1]);
                 *reinterpret_cast<uint2*>(a_hi + off) = *reinterpret_cast<uint2*>(hp);
                 if (NSPLIT > 1) {
-                    __half2 lp[2] = {__halves2half2(half_sat(a.x - __half2float(h0)),
-                                                    half_sat(a.y - __half2float(h1))),
-                                     __halves2half2(half_sat(a.z - __half2float(h2)),
-                                                    half_sat(a.w - __half2float(h3)))};
+                    __half2 lp[2] = {half2_sat(a.x - __half2float(h0), a.y - __half2float(h1)),
+                                     half2_sat(a.z - __half2float(h2), a.w - __half2float(h3))};
                     *reinterpret_cast<uint2*>(a_lo + off) = *reinterpret_cast<uint2*>(lp);
                 }
             }

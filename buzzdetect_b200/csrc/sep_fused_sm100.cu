@@ -101,13 +101,13 @@ __device__ __forceinline__ void store_a(uint32_t a_hi, uint32_t a_lo, uint32_t r
     a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
     const uint32_t rowoff = (row >> 3) * 1024u + (row & 7u) * 128u;
     const uint32_t off = rowoff + ((chunk ^ (row & 7u)) << 4) + half8;
-    const __half h0 = half_sat(a.x), h1 = half_sat(a.y);
-    const __half h2 = half_sat(a.z), h3 = half_sat(a.w);
-    __half2 hp[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
+    __half2 hp[2] = {half2_sat(a.x, a.y), half2_sat(a.z, a.w)};
+    const __half h0 = __low2half(hp[0]), h1 = __high2half(hp[0]);
+    const __half h2 = __low2half(hp[1]), h3 = __high2half(hp[1]);
     sts64(a_hi + off, reinterpret_cast<uint32_t*>(hp)[0], reinterpret_cast<uint32_t*>(hp)[1]);
     if (NSPLIT == 3) {
-        __half2 lp[2] = {__halves2half2(half_sat(a.x - __half2float(h0)), half_sat(a.y - __half2float(h1))),
-                         __halves2half2(half_sat(a.z - __half2float(h2)), half_sat(a.w - __half2float(h3)))};
+        __half2 lp[2] = {half2_sat(a.x - __half2float(h0), a.y - __half2float(h1)),
+                         half2_sat(a.z - __half2float(h2), a.w - __half2float(h3))};
         sts64(a_lo + off, reinterpret_cast<uint32_t*>(lp)[0], reinterpret_cast<uint32_t*>(lp)[1]);
     }
     if (NSPLIT == 2) {
