@@ -213,7 +213,7 @@ l12_fused2_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_con
                         float4 a = acc[o][r];
                         a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
                         const uint32_t row = static_cast<uint32_t>((2 * brow + o) * 32 + ws * 4 + r);
-                        const uint32_t off = (row >> 3) * 1024u + (row & 7u) * 128u + ((chunk ^ (row & 7u)) << 4) +
+                        const uint32_t off = (row << 7) + ((chunk ^ (row & 7u)) << 4) +        // row * 128 = 8-row groups of 1 KB
                                              (static_cast<uint32_t>(quad & 1) << 3);
                         __half2 hp[2] = {half2_sat(a.x, a.y), half2_sat(a.z, a.w)};
                         const __half h0 = __low2half(hp[0]), h1 = __high2half(hp[0]);

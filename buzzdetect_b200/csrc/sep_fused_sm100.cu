@@ -99,7 +99,7 @@ template <int NSPLIT>
 __device__ __forceinline__ void store_a(uint32_t a_hi, uint32_t a_lo, uint32_t row, uint32_t chunk, uint32_t half8,
                                         uint32_t c8chunk, uint32_t c8off, float4 a) {
     a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
-    const uint32_t rowoff = (row >> 3) * 1024u + (row & 7u) * 128u;
+    const uint32_t rowoff = row << 7;                  // = (row >> 3) * 1024 + (row & 7) * 128: 8-row groups of 1 KB, 128-byte rows
     const uint32_t off = rowoff + ((chunk ^ (row & 7u)) << 4) + half8;
     __half2 hp[2] = {half2_sat(a.x, a.y), half2_sat(a.z, a.w)};
     const __half h0 = __low2half(hp[0]), h1 = __high2half(hp[0]);
