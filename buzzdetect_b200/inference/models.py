@@ -1,4 +1,7 @@
-"""Model plugin surface -- mirrors the reference's src/inference/models.py:12-79 (BaseModel, load_model)."""
+"""Boundary shim, not built work: the reference's plugin interface src/inference/models.py:12-79 (BaseModel, load_model) kept VERBATIM in names,
+attributes, argument meaning and discovery rules, so that the plugins behave identically when they are loaded by the
+reference's own module instead (inside a buzzdetect checkout they import `src.inference.*` first; see
+tests/test_reference_interop.py::test_plugins_load_through_the_reference_loader)."""
 import importlib.util
 import json
 import os

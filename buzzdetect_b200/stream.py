@@ -5,6 +5,12 @@ Mirrors, with the same float expressions so indices agree bit for bit:
   * gaps_to_chunklist                src/stream/results_coverage.py:59-70 (np.arange + round to 2 decimals)
   * melt_coverage / get_gaps / smooth_gaps  src/stream/results_coverage.py:4-56 (resume: what is still to do)
   * WorkerStreamer.queue_chunk       src/stream/worker.py:110-112 (sample_from = int(chunk[0]*sr) on python floats)
+
+gaps_to_chunklist, get_gaps and smooth_gaps keep the reference's float expressions VERBATIM on purpose: chunk boundaries
+and resume gaps must agree bit for bit with a run of the reference on the same partial file, and any re-association of
+the arithmetic would move a boundary by an ulp.  They are checked against the imported reference module
+(tests/test_reference_interop.py::test_resume_math_matches_reference_results_coverage); melt_coverage is a pandas-free
+rewrite checked the same way.
 """
 from __future__ import annotations
 
