@@ -2,7 +2,6 @@
 attributes, argument meaning and discovery rules, so that the plugins behave identically when they are loaded by the
 reference's own module instead (inside a buzzdetect checkout they import `src.inference.*` first; see
 tests/test_reference_interop.py::test_plugins_load_through_the_reference_loader)."""
-src/inference/embedding.py:8-79 (BaseEmbedder, load_embedder)."""
 import importlib.util
 from abc import ABC, abstractmethod
 from pathlib import Path
